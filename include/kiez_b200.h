@@ -1,0 +1,197 @@
+/*
+ * kiez_b200 -- C ABI of the B200 (sm_100a) exact-kNN + hubness-reduction hot path.
+ *
+ * The reference (dobraczka/kiez v0.5.0) is pure Python: it has no FFI.  Its
+ * boundary for this path is the NNAlgorithm / HubnessReduction plugin interface
+ * (kiez/neighbors/neighbor_algorithm_base.py:13-136,
+ *  kiez/hubness_reduction/base.py:17-105).  The entry points below are what the
+ * thin Python host classes in kiez_b200/ bind with ctypes; each one names the
+ * reference code it replaces.  INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions: extern "C"; raw DEVICE pointers + sizes; the caller owns every
+ * buffer; no hidden allocation except where stated; everything is enqueued on
+ * `stream` (a cudaStream_t passed as void*) without host synchronisation unless
+ * stated; return value 0 = ok, non-zero = error with a thread-local message in
+ * kb2_last_error().  Row-major, C-contiguous unless a leading dimension is given.
+ * Distances cross the boundary as float64, neighbour ids as int64 -- the dtypes
+ * the reference's SklearnNN path returns.
+ */
+#ifndef KIEZ_B200_H
+#define KIEZ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KB2_VERSION 1
+
+/* metric codes (kiez SklearnNN metric names; minkowski/l2 are p=2 euclidean) */
+#define KB2_METRIC_EUCLIDEAN   0
+#define KB2_METRIC_SQEUCLIDEAN 1
+#define KB2_METRIC_COSINE      2
+
+/* rescale modes */
+#define KB2_RESCALE_CSLS      0 /* kiez/hubness_reduction/csls.py:85-96            */
+#define KB2_RESCALE_LS        1 /* local_scaling.py:135-140 (method ls/standard)   */
+#define KB2_RESCALE_NICDM     2 /* local_scaling.py:142-147 (method nicdm)         */
+#define KB2_RESCALE_MP_GAUSS  3 /* mutual_proximity.py:166-183, numpy branch       */
+
+/* which candidate-search kernel kb2_knn_candidates runs */
+#define KB2_KNN_AUTO  0 /* tcgen05 */
+#define KB2_KNN_TC    1 /* tcgen05/TMEM 3xTF32 tiles fed by TMA                  */
+#define KB2_KNN_SIMT  2 /* fp32 FFMA tiles; cross-check + debugging aid          */
+
+int kb2_version(void);
+const char *kb2_last_error(void);
+
+/* Widest candidate list (per query row, per split) the search kernels support. */
+int kb2_max_candidates(void);
+/* Padded feature count the prepared operands use for a raw feature count d. */
+int kb2_padded_dim(int d);
+/* Suggested number of index splits for nq queries (fills the SMs when nq is small). */
+int kb2_suggest_splits(int64_t nq, int64_t ny, int cap, int sm_count);
+
+/*
+ * "Index build" -- replaces SklearnNN._fit / NearestNeighbors.fit
+ * (kiez/neighbors/exact/sklearn_nearest_neighbors.py:83-94), which for brute
+ * force only keeps the matrix.  Produces the operands the tensor-core search
+ * reads: the 3xTF32 split  x = hi + lo  (hi = rn_tf32(x), lo = rn_tf32(x-hi)),
+ * zero-padded to dpad columns, plus the per-row selection term
+ * (||x||^2 for euclidean, 0 for cosine where rows are L2-normalised first).
+ *   x        [n][ldx] fp32 (first d columns used)
+ *   center   [d] fp32 or NULL: subtracted from every row first (distances are
+ *            translation invariant; keeps the expanded form well conditioned)
+ *   hi, lo   [n][dpad] fp32 out
+ *   key_term [n] fp32 out
+ *   sqnorm   [n] fp64 out or NULL: exact ||x||^2 of the *raw* rows (cosine finish)
+ */
+int kb2_prepare_rows(const float *x, int64_t n, int d, int64_t ldx, const float *center,
+                     int metric, float *hi, float *lo, int dpad, float *key_term,
+                     double *sqnorm, void *stream);
+
+/*
+ * Candidate search -- the contraction of ArgKmin / pairwise_distances_chunked
+ * behind NearestNeighbors.kneighbors (sklearn_nearest_neighbors.py:96-101,
+ * reached from neighbor_algorithm_base.py:116-136) without ever materialising
+ * the nq x ny matrix.  For every query row it keeps the `cap` smallest
+ * selection keys  key = y_key[col] - 2 <q,y_col>  per index split.
+ *   q_hi,q_lo [nq][dpad], y_hi,y_lo [ny][dpad], y_key [ny]
+ *   splits    >=1: the index rows are cut into `splits` contiguous ranges, each
+ *             searched by its own CTA set (fills the GPU when nq is small)
+ *   exclude_self: drop column j where j + self_offset == row (sklearn X=None
+ *             semantics, neighbors/_base.py:937-958)
+ *   cand_idx  [nq][splits*cap] int32 out: LOCAL index row ids, -1 = empty slot
+ *   cand_key  [nq][splits*cap] fp32 out or NULL (approximate keys; tests only)
+ */
+int kb2_knn_candidates(int impl, const float *q_hi, const float *q_lo, int64_t nq,
+                       const float *y_hi, const float *y_lo, const float *y_key,
+                       int64_t ny, int dpad, int cap, int splits, int exclude_self,
+                       int64_t self_offset, int32_t *cand_idx, float *cand_key,
+                       void *stream);
+
+/*
+ * Exact finish -- recomputes the distance of every candidate in float64 from
+ * the raw fp32 rows (the oracle upcasts fp32 to fp64 too,
+ * sklearn _middle_term_computer.pyx.tp:309-318), sorts (distance, id)
+ * ascending and writes the best k: the (dist, ind) pair NNAlgorithm._kneighbors
+ * must return (neighbor_algorithm_base.py:112-136).
+ *   q, y     raw rows, elem_size 4 (fp32) or 8 (fp64: float64 callers such as the
+ *            README example keep their exact values for the finish)
+ *   cand_idx [nq][ncand] local ids (-1 skipped); index_base is added on output
+ *   q_sqnorm,y_sqnorm: fp64 ||.||^2 of the raw rows, cosine only (else NULL)
+ */
+int kb2_refine_topk(const void *q, int64_t nq, int64_t ldq, const void *y, int64_t ny,
+                    int64_t ldy, int d, int elem_size, const double *q_sqnorm,
+                    const double *y_sqnorm, const int32_t *cand_idx, int ncand, int metric,
+                    int64_t index_base, int k, double *out_dist, int64_t *out_ind, void *stream);
+
+/*
+ * Row-wise top-k of (dist, ind) pairs, ascending, ties by input position, NaN last.
+ * Replaces HubnessReduction._sort (kiez/hubness_reduction/base.py:72-87) and is the
+ * multi-GPU merge kernel: with nparts > 1 row r is the concatenation of
+ * dist[p*part_stride + r*c .. +c) for p in [0, nparts).
+ */
+int kb2_topk_rows(const double *dist, const int64_t *ind, int64_t n, int c, int nparts,
+                  int64_t part_stride, int k, double *out_dist, int64_t *out_ind,
+                  void *stream);
+
+/* Per-row statistics of the reverse neighbourhoods (CSLS/NICDM mean, LS c-th
+ * neighbour, MutualProximity mu/sigma with ddof=0: csls.py:90,
+ * local_scaling.py:136,143, mutual_proximity.py:101-103).  Any output may be NULL. */
+int kb2_row_stats(const double *dist, int64_t n, int c, double *mean, double *sd,
+                  double *last, void *stream);
+
+/*
+ * Rescale + final sort, one pass: out = top-k over the c candidates of
+ *   CSLS     2 d - mean_c(d_row) - stat_a[ind]
+ *   LS       1 - exp(-d^2 / (d_row[c-1] * stat_a[ind]))
+ *   NICDM    d / sqrt(mean_c(d_row) * stat_a[ind])
+ *   MP_GAUSS 1 - sf(d; mu_row, sd_row) * sf(d; stat_a[ind], stat_b[ind])
+ * k == 0: write the unsorted (n, c) transform (HubnessReduction.transform contract).
+ */
+int kb2_rescale_topk(int mode, const double *dist, const int64_t *ind, int64_t n, int c,
+                     const double *stat_a, const double *stat_b, int64_t n_stats, int k,
+                     double *out_dist, int64_t *out_ind, void *stream);
+
+/* MutualProximity(method="empiric") transform, mutual_proximity.py:185-212,
+ * including its source-id / target-id index-space mix, as c x c membership
+ * tests instead of an O(max_ind) table per pair. */
+int kb2_mp_empiric_topk(const double *dist, const int64_t *ind, int64_t n, int c,
+                        const double *rev_dist, const int64_t *rev_ind, int64_t m,
+                        int c_rev, int k, double *out_dist, int64_t *out_ind, void *stream);
+
+/* DisSimLocal._fit (dis_sim.py:95-108): centroid of the c_rev reverse neighbours
+ * (source rows) of every target row and ||target - centroid||^2, in fp64.
+ *   centroids [m][d] fp64 out or NULL, dist_to_cent [m] fp64 out */
+int kb2_dsl_fit(const void *source, int64_t n_source, int64_t lds, const void *target,
+                int64_t m, int64_t ldt, int d, int elem_size, const int64_t *rev_ind, int c_rev,
+                double *centroids, double *dist_to_cent, void *stream);
+
+/* DisSimLocal.transform (dis_sim.py:139-181), stage 1: raw (n, c) values
+ * ||q-t||^2 - ||q-c_q||^2 - dist_to_cent[ind] and their global minimum
+ * (*global_min must be initialised to +inf by the caller; with row-sharded
+ * multi-GPU runs all-reduce(min) it before stage 2). */
+int kb2_dsl_transform(const void *query, int64_t n, int64_t ldq, const void *target,
+                      int64_t m, int64_t ldt, int d, int elem_size, const int64_t *ind, int c,
+                      const double *dist_to_cent, double *raw, double *global_min,
+                      void *stream);
+/* stage 2: shift by -min if negative, sqrt unless squared, top-k (k==0: unsorted). */
+int kb2_dsl_finish_topk(const double *raw, const int64_t *ind, int64_t n, int c,
+                        const double *global_min, int squared, int k, double *out_dist,
+                        int64_t *out_ind, void *stream);
+
+/*
+ * kiez.analysis.hubness_score (kiez/analysis/estimation.py:272-351) on device.
+ * kb2_index_range: min and max id over the first k columns -> out[2] (device).
+ * kb2_k_occurrence: bincount of the first k columns, negatives dropped (:286-295).
+ * kb2_hub_moments: one pass over the histogram; out[0..9] (device, fp64) =
+ *   sum, sum (x-mean)^2, sum (x-mean)^3, sum |x-mean|, sum sqrt(x), max,
+ *   #zeros (antihubs), #(x >= hub_thresh) (hubs), sum x over hubs, sum x^2
+ * kb2_compact_ids: ascending ids whose count is ==0 (mode 0) or >= thresh (mode 1);
+ *   scratch must hold (nbins+1023)/1024 + 1 int64; *out_count receives the total.
+ * kb2_gini_numerator: sum_ij |x_i - x_j| exactly (int64) via a value histogram;
+ *   scratch must hold max_value+1 int64.
+ */
+int kb2_index_range(const int64_t *ind, int64_t n, int64_t ld, int k, int64_t *out,
+                    void *stream);
+int kb2_k_occurrence(const int64_t *ind, int64_t n, int64_t ld, int k, int64_t nbins,
+                     int64_t *hist, void *stream);
+int kb2_hub_moments(const int64_t *hist, int64_t nbins, double mean, double hub_thresh,
+                    double *out, void *stream);
+int kb2_compact_ids(const int64_t *hist, int64_t nbins, int mode, double thresh,
+                    int64_t *scratch, int64_t *out_ids, int64_t *out_count, void *stream);
+int kb2_gini_numerator(const int64_t *hist, int64_t nbins, int64_t max_value,
+                       int64_t *scratch, int64_t *out, void *stream);
+
+/* kiez.evaluate.hits (kiez/evaluate/eval_metrics.py:23-61): for each of nks
+ * cut-offs ks[i], the number of rows r with gold[r] among ind[r][0..ks[i]).
+ * gold[r] < 0 = row not evaluated.  counts [nks] int64 (device) is accumulated into. */
+int kb2_hits(const int64_t *ind, int64_t n, int64_t ld, int k, const int64_t *gold,
+             const int32_t *ks, int nks, int64_t *counts, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KIEZ_B200_H */

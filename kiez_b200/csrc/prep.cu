@@ -1,0 +1,74 @@
+// "Index build": 3xTF32 operand split + selection term + exact norms.
+// Replaces SklearnNN._fit (kiez/neighbors/exact/sklearn_nearest_neighbors.py:83-94).
+#include "common.cuh"
+
+namespace kb2 {
+
+__device__ __forceinline__ float to_tf32_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// One warp per row.  HBM-bound: reads d*4 B, writes 2*dpad*4 + 12 B per row.
+__global__ void __launch_bounds__(256)
+prepare_rows_kernel(const float *__restrict__ x, int64_t n, int d, int64_t ldx,
+                    const float *__restrict__ center, int normalize, float *__restrict__ hi,
+                    float *__restrict__ lo, int dpad, float *__restrict__ key_term,
+                    double *__restrict__ sqnorm) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const float *xr = x + row * ldx;
+    double raw2 = 0.0;   // ||x||^2 of the raw row, fp64
+    double cen2 = 0.0;   // ||x - center||^2, fp64
+    for (int j = lane; j < d; j += 32) {
+        const float v = xr[j];
+        raw2 += (double)v * (double)v;
+        const float w = center ? v - center[j] : v;
+        cen2 += (double)w * (double)w;
+    }
+    raw2 = warp_sum(raw2);
+    cen2 = warp_sum(cen2);
+    float scale = 1.0f;
+    if (normalize) scale = cen2 > 0.0 ? (float)(1.0 / sqrt(cen2)) : 1.0f;
+    float *hr = hi + row * dpad;
+    float *lr = lo + row * dpad;
+    for (int j = lane; j < dpad; j += 32) {
+        float h = 0.f, l = 0.f;
+        if (j < d) {
+            float w = xr[j];
+            if (center) w -= center[j];
+            w *= scale;
+            h = to_tf32_rn(w);
+            l = to_tf32_rn(w - h);
+        }
+        hr[j] = h;
+        lr[j] = l;
+    }
+    if (lane == 0) {
+        key_term[row] = normalize ? 0.0f : (float)cen2;
+        if (sqnorm) sqnorm[row] = raw2;
+    }
+}
+
+}  // namespace kb2
+
+extern "C" int kb2_padded_dim(int d) { return ((d + 31) / 32) * 32; }
+
+extern "C" int kb2_prepare_rows(const float *x, int64_t n, int d, int64_t ldx,
+                                const float *center, int metric, float *hi, float *lo,
+                                int dpad, float *key_term, double *sqnorm, void *stream) {
+    KB2_CHECK(n >= 0 && d > 0 && ldx >= d, "prepare_rows: bad shape n=%lld d=%d ldx=%lld",
+              (long long)n, d, (long long)ldx);
+    KB2_CHECK(dpad == kb2_padded_dim(d), "prepare_rows: dpad=%d, expected %d", dpad,
+              kb2_padded_dim(d));
+    KB2_CHECK(metric >= 0 && metric <= 2, "prepare_rows: unknown metric %d", metric);
+    if (n == 0) return 0;
+    const int warps = 8;
+    const int64_t blocks = kb2::ceil_div64(n, warps);
+    kb2::prepare_rows_kernel<<<(unsigned)blocks, warps * 32, 0, (cudaStream_t)stream>>>(
+        x, n, d, ldx, center, metric == KB2_METRIC_COSINE, hi, lo, dpad, key_term, sqnorm);
+    KB2_LAUNCH_CHECK();
+    return 0;
+}

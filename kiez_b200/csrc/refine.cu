@@ -1,0 +1,183 @@
+// Exact float64 finish of the candidate lists, and the generic row-wise top-k
+// (final hubness sort + multi-GPU merge).
+#include "common.cuh"
+
+namespace kb2 {
+
+constexpr int REFINE_WARPS = 4;
+
+// One warp per query row: gather each candidate's raw fp32 row, accumulate the
+// distance in fp64, then bitonic-sort (dist, id) in shared memory and write the
+// best k.  HBM/L2-bound on the row gathers (ncand * d * 4 B per query).
+template <typename T, bool VEC4>
+__global__ void __launch_bounds__(REFINE_WARPS * 32)
+refine_topk_kernel(const T *__restrict__ q, int64_t nq, int64_t ldq,
+                   const T *__restrict__ y, int64_t ny, int64_t ldy, int d,
+                   const double *__restrict__ q_sqnorm, const double *__restrict__ y_sqnorm,
+                   const int32_t *__restrict__ cand_idx, int ncand, int P, int metric,
+                   int64_t index_base, int k, double *__restrict__ out_dist,
+                   int64_t *__restrict__ out_ind) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *key = reinterpret_cast<double *>(smem_raw) + (size_t)warp * P;
+    int64_t *tie = reinterpret_cast<int64_t *>(reinterpret_cast<double *>(smem_raw) +
+                                               (size_t)REFINE_WARPS * P) + (size_t)warp * P;
+    const int64_t row = (int64_t)blockIdx.x * REFINE_WARPS + warp;
+    if (row >= nq) return;
+    const T *qr = q + row * ldq;
+    const int32_t *cr = cand_idx + row * (int64_t)ncand;
+    for (int j = 0; j < P; ++j) {
+        const int32_t id = (j < ncand) ? cr[j] : -1;
+        double dist = INFINITY;
+        if (id >= 0 && id < ny) {
+            const T *yr = y + (int64_t)id * ldy;
+            double acc = 0.0;
+            if (metric == KB2_METRIC_COSINE) {
+                if constexpr (VEC4) {
+                    for (int t = lane * 4; t < d; t += 128) {
+                        const float4 a = *reinterpret_cast<const float4 *>(qr + t);
+                        const float4 b = *reinterpret_cast<const float4 *>(yr + t);
+                        acc += (double)a.x * b.x + (double)a.y * b.y + (double)a.z * b.z +
+                               (double)a.w * b.w;
+                    }
+                } else {
+                    for (int t = lane; t < d; t += 32) acc += (double)qr[t] * (double)yr[t];
+                }
+                acc = warp_sum(acc);
+                double nq2 = q_sqnorm[row], ny2 = y_sqnorm[id];
+                const double nx = nq2 > 0.0 ? sqrt(nq2) : 1.0;
+                const double nyv = ny2 > 0.0 ? sqrt(ny2) : 1.0;
+                dist = 1.0 - acc / (nx * nyv);
+                dist = fmin(fmax(dist, 0.0), 2.0);
+            } else {
+                if constexpr (VEC4) {
+                    for (int t = lane * 4; t < d; t += 128) {
+                        const float4 a = *reinterpret_cast<const float4 *>(qr + t);
+                        const float4 b = *reinterpret_cast<const float4 *>(yr + t);
+                        const double dx = (double)a.x - (double)b.x, dy = (double)a.y - (double)b.y,
+                                     dz = (double)a.z - (double)b.z, dw = (double)a.w - (double)b.w;
+                        acc += dx * dx + dy * dy + dz * dz + dw * dw;
+                    }
+                } else {
+                    for (int t = lane; t < d; t += 32) {
+                        const double dx = (double)qr[t] - (double)yr[t];
+                        acc += dx * dx;
+                    }
+                }
+                acc = warp_sum(acc);
+                dist = (metric == KB2_METRIC_EUCLIDEAN) ? sqrt(acc) : acc;
+            }
+        }
+        if (lane == 0) {
+            key[j] = dist;
+            tie[j] = (id >= 0 && id < ny) ? (int64_t)id + index_base : INT64_MAX;
+        }
+    }
+    warp_bitonic_sort(key, tie, nullptr, P, lane);
+    for (int j = lane; j < k; j += 32) {
+        out_dist[row * k + j] = key[j];
+        out_ind[row * k + j] = (tie[j] == INT64_MAX) ? -1 : tie[j];
+    }
+}
+
+// Row-wise top-k of (dist, ind): one warp per row, bitonic sort in smem keyed by
+// (dist, input position) so that ties resolve like a stable argsort.
+__global__ void __launch_bounds__(REFINE_WARPS * 32)
+topk_rows_kernel(const double *__restrict__ dist, const int64_t *__restrict__ ind, int64_t n, int c,
+                 int nparts, int64_t part_stride, int P, int k, double *__restrict__ out_dist,
+                 int64_t *__restrict__ out_ind) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *key = reinterpret_cast<double *>(smem_raw) + (size_t)warp * P;
+    int64_t *tie = reinterpret_cast<int64_t *>(reinterpret_cast<double *>(smem_raw) +
+                                               (size_t)REFINE_WARPS * P) + (size_t)warp * P;
+    int64_t *pay = reinterpret_cast<int64_t *>(reinterpret_cast<double *>(smem_raw) +
+                                               (size_t)2 * REFINE_WARPS * P) + (size_t)warp * P;
+    const int64_t row = (int64_t)blockIdx.x * REFINE_WARPS + warp;
+    if (row >= n) return;
+    const int total = c * nparts;
+    for (int j = lane; j < P; j += 32) {
+        if (j < total) {
+            const int part = j / c, w = j - part * c;
+            const int64_t o = (int64_t)part * part_stride + row * c + w;
+            key[j] = dist[o];
+            pay[j] = ind[o];
+            tie[j] = j;
+        } else {
+            key[j] = __longlong_as_double(0x7ff8000000000000LL);   // NaN pad sorts last
+            pay[j] = -1;
+            tie[j] = INT64_MAX;
+        }
+    }
+    warp_bitonic_sort(key, tie, pay, P, lane);
+    for (int j = lane; j < k; j += 32) {
+        out_dist[row * k + j] = key[j];
+        out_ind[row * k + j] = pay[j];
+    }
+}
+
+}  // namespace kb2
+
+template <typename T, bool VEC4>
+static int launch_refine(const void *q, int64_t nq, int64_t ldq, const void *y, int64_t ny,
+                         int64_t ldy, int d, const double *q_sqnorm, const double *y_sqnorm,
+                         const int32_t *cand_idx, int ncand, int P, int metric, int64_t index_base,
+                         int k, double *out_dist, int64_t *out_ind, cudaStream_t st) {
+    using namespace kb2;
+    const size_t smem = (size_t)REFINE_WARPS * P * 16;
+    KB2_CUDA(cudaFuncSetAttribute(refine_topk_kernel<T, VEC4>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    refine_topk_kernel<T, VEC4><<<(unsigned)ceil_div64(nq, REFINE_WARPS), REFINE_WARPS * 32, smem, st>>>(
+        static_cast<const T *>(q), nq, ldq, static_cast<const T *>(y), ny, ldy, d, q_sqnorm, y_sqnorm,
+        cand_idx, ncand, P, metric, index_base, k, out_dist, out_ind);
+    KB2_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int kb2_refine_topk(const void *q, int64_t nq, int64_t ldq, const void *y, int64_t ny,
+                               int64_t ldy, int d, int elem_size, const double *q_sqnorm,
+                               const double *y_sqnorm, const int32_t *cand_idx, int ncand,
+                               int metric, int64_t index_base, int k, double *out_dist,
+                               int64_t *out_ind, void *stream) {
+    using namespace kb2;
+    KB2_CHECK(nq >= 0 && ny > 0 && d > 0 && ldq >= d && ldy >= d, "refine_topk: bad shape");
+    KB2_CHECK(elem_size == 4 || elem_size == 8, "refine_topk: elem_size must be 4 (fp32) or 8 (fp64)");
+    KB2_CHECK(ncand > 0 && ncand <= 2048, "refine_topk: ncand=%d outside (0, 2048]", ncand);
+    KB2_CHECK(k > 0 && k <= ncand, "refine_topk: k=%d must be in (0, ncand=%d]", k, ncand);
+    KB2_CHECK(metric >= 0 && metric <= 2, "refine_topk: unknown metric %d", metric);
+    KB2_CHECK(metric != KB2_METRIC_COSINE || (q_sqnorm && y_sqnorm),
+              "refine_topk: cosine needs q_sqnorm and y_sqnorm");
+    if (nq == 0) return 0;
+    const int P = next_pow2(ncand);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (elem_size == 8)
+        return launch_refine<double, false>(q, nq, ldq, y, ny, ldy, d, q_sqnorm, y_sqnorm, cand_idx,
+                                            ncand, P, metric, index_base, k, out_dist, out_ind, st);
+    const bool vec = (d % 4 == 0) && (ldq % 4 == 0) && (ldy % 4 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(y)) % 16 == 0);
+    if (vec)
+        return launch_refine<float, true>(q, nq, ldq, y, ny, ldy, d, q_sqnorm, y_sqnorm, cand_idx,
+                                          ncand, P, metric, index_base, k, out_dist, out_ind, st);
+    return launch_refine<float, false>(q, nq, ldq, y, ny, ldy, d, q_sqnorm, y_sqnorm, cand_idx, ncand,
+                                       P, metric, index_base, k, out_dist, out_ind, st);
+}
+
+extern "C" int kb2_topk_rows(const double *dist, const int64_t *ind, int64_t n, int c, int nparts,
+                             int64_t part_stride, int k, double *out_dist, int64_t *out_ind,
+                             void *stream) {
+    using namespace kb2;
+    KB2_CHECK(n >= 0 && c > 0 && nparts > 0, "topk_rows: bad shape");
+    const int total = c * nparts;
+    KB2_CHECK(total <= 2048, "topk_rows: %d candidates per row exceed 2048", total);
+    KB2_CHECK(k > 0 && k <= total, "topk_rows: k=%d must be in (0, %d]", k, total);
+    if (n == 0) return 0;
+    const int P = next_pow2(total);
+    const size_t smem = (size_t)REFINE_WARPS * P * 24;
+    KB2_CUDA(cudaFuncSetAttribute(topk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    topk_rows_kernel<<<(unsigned)ceil_div64(n, REFINE_WARPS), REFINE_WARPS * 32, smem,
+                       (cudaStream_t)stream>>>(dist, ind, n, c, nparts, part_stride, P, k, out_dist,
+                                               out_ind);
+    KB2_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,456 @@
+// Hubness-reduction rescaling of the candidate distances, fused with the final
+// top-k sort.  All kernels are one-warp-per-row, float64, HBM-bound: they stream
+// the (n, c) candidate arrays once, gather 1-2 per-target statistics per element
+// and write (n, k).
+//   CSLS        kiez/hubness_reduction/csls.py:85-96
+//   LS / NICDM  kiez/hubness_reduction/local_scaling.py:129-151
+//   MP Gaussian kiez/hubness_reduction/mutual_proximity.py:166-183 (numpy branch:
+//               nanmean / nanstd ddof=0 / scipy.stats.norm.sf)
+//   MP empiric  kiez/hubness_reduction/mutual_proximity.py:185-212
+//   DisSimLocal kiez/hubness_reduction/dis_sim.py:95-108,139-181
+#include "common.cuh"
+
+namespace kb2 {
+
+constexpr int RS_WARPS = 4;
+
+struct RowBuf {
+    double *key;
+    int64_t *tie;
+    int64_t *pay;
+};
+__device__ __forceinline__ RowBuf row_buf(unsigned char *smem_raw, int warp, int P) {
+    RowBuf b;
+    b.key = reinterpret_cast<double *>(smem_raw) + (size_t)warp * P;
+    b.tie = reinterpret_cast<int64_t *>(reinterpret_cast<double *>(smem_raw) + (size_t)RS_WARPS * P) +
+            (size_t)warp * P;
+    b.pay = reinterpret_cast<int64_t *>(reinterpret_cast<double *>(smem_raw) + (size_t)2 * RS_WARPS * P) +
+            (size_t)warp * P;
+    return b;
+}
+
+// nan-skipping mean / population std of a row held in smem (numpy nanmean/nanstd)
+__device__ __forceinline__ void row_mean_sd(const double *v, int c, int lane, double &mean,
+                                            double &sd) {
+    double s = 0.0, cnt = 0.0;
+    for (int j = lane; j < c; j += 32) {
+        const double x = v[j];
+        if (!isnan(x)) { s += x; cnt += 1.0; }
+    }
+    s = warp_sum(s);
+    cnt = warp_sum(cnt);
+    mean = s / cnt;
+    double q = 0.0;
+    for (int j = lane; j < c; j += 32) {
+        const double x = v[j];
+        if (!isnan(x)) { const double e = x - mean; q += e * e; }
+    }
+    q = warp_sum(q);
+    sd = sqrt(q / cnt);
+}
+
+__device__ __forceinline__ double norm_sf(double x, double mu, double sd) {
+    if (!(sd > 0.0)) return __longlong_as_double(0x7ff8000000000000LL);   // scipy: scale <= 0 -> nan
+    return 0.5 * erfc(((x - mu) / sd) * 0.70710678118654752440);
+}
+
+// write the row either unsorted (k == 0: the HubnessReduction.transform contract)
+// or as its k best after a bitonic sort keyed by (value, position)
+__device__ __forceinline__ void emit_row(RowBuf b, int c, int P, int k, int64_t row, int lane,
+                                         double *out_dist, int64_t *out_ind) {
+    if (k == 0) {
+        __syncwarp();
+        for (int j = lane; j < c; j += 32) {
+            out_dist[row * c + j] = b.key[j];
+            out_ind[row * c + j] = b.pay[j];
+        }
+        return;
+    }
+    for (int j = c + lane; j < P; j += 32) {
+        b.key[j] = __longlong_as_double(0x7ff8000000000000LL);
+        b.tie[j] = INT64_MAX;
+        b.pay[j] = -1;
+    }
+    warp_bitonic_sort(b.key, b.tie, b.pay, P, lane);
+    for (int j = lane; j < k; j += 32) {
+        out_dist[row * k + j] = b.key[j];
+        out_ind[row * k + j] = b.pay[j];
+    }
+}
+
+__global__ void __launch_bounds__(RS_WARPS * 32)
+row_stats_kernel(const double *__restrict__ dist, int64_t n, int c, double *__restrict__ mean,
+                 double *__restrict__ sd, double *__restrict__ last) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * RS_WARPS + warp;
+    if (row >= n) return;
+    const double *r = dist + row * c;
+    // plain mean (CSLS/NICDM use ndarray.mean) and nan-aware mean/std (MP uses nanmean/nanstd)
+    double s = 0.0, sn = 0.0, cnt = 0.0;
+    for (int j = lane; j < c; j += 32) {
+        const double x = r[j];
+        s += x;
+        if (!isnan(x)) { sn += x; cnt += 1.0; }
+    }
+    s = warp_sum(s);
+    sn = warp_sum(sn);
+    cnt = warp_sum(cnt);
+    const double mu = sn / cnt;
+    double q = 0.0;
+    for (int j = lane; j < c; j += 32) {
+        const double x = r[j];
+        if (!isnan(x)) { const double e = x - mu; q += e * e; }
+    }
+    q = warp_sum(q);
+    if (lane == 0) {
+        // `mean` serves CSLS/NICDM when sd == nullptr, MutualProximity otherwise
+        if (mean) mean[row] = sd ? mu : s / (double)c;
+        if (sd) sd[row] = sqrt(q / cnt);
+        if (last) last[row] = r[c - 1];
+    }
+}
+
+__global__ void __launch_bounds__(RS_WARPS * 32)
+rescale_topk_kernel(int mode, const double *__restrict__ dist, const int64_t *__restrict__ ind,
+                    int64_t n, int c, const double *__restrict__ stat_a,
+                    const double *__restrict__ stat_b, int64_t n_stats, int P, int k,
+                    double *__restrict__ out_dist, int64_t *__restrict__ out_ind) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * RS_WARPS + warp;
+    if (row >= n) return;
+    RowBuf b = row_buf(smem_raw, warp, P);
+    const double *dr = dist + row * c;
+    const int64_t *ir = ind + row * c;
+    double s = 0.0;
+    for (int j = lane; j < c; j += 32) {
+        const double x = dr[j];
+        b.key[j] = x;
+        b.pay[j] = ir[j];
+        b.tie[j] = j;
+        s += x;
+    }
+    s = warp_sum(s);
+    __syncwarp();
+    const double mean = s / (double)c;
+    const double last = b.key[c - 1];
+    double mu = 0.0, sd = 0.0;
+    if (mode == KB2_RESCALE_MP_GAUSS) row_mean_sd(b.key, c, lane, mu, sd);
+    __syncwarp();
+    for (int j = lane; j < c; j += 32) {
+        const double x = b.key[j];
+        const int64_t id = b.pay[j];
+        const bool ok = id >= 0 && id < n_stats;
+        const double a = ok ? stat_a[id] : __longlong_as_double(0x7ff8000000000000LL);
+        double r;
+        if (mode == KB2_RESCALE_CSLS) {
+            r = 2.0 * x - mean - a;
+        } else if (mode == KB2_RESCALE_LS) {
+            r = 1.0 - exp(-1.0 * (x * x) / (last * a));
+        } else if (mode == KB2_RESCALE_NICDM) {
+            r = x / sqrt(mean * a);
+        } else {
+            const double sb = ok ? stat_b[id] : __longlong_as_double(0x7ff8000000000000LL);
+            r = 1.0 - norm_sf(x, mu, sd) * norm_sf(x, a, sb);
+        }
+        b.key[j] = r;
+    }
+    emit_row(b, c, P, k, row, lane, out_dist, out_ind);
+}
+
+// MutualProximity empiric: for candidate j of query i (target id cj):
+//   d_j[l] = rev_dist[cj][p] if ind[i][l] == rev_ind[cj][p] (last p wins) else rev_dist[cj][-1]+1e-6
+//   out[j] = 1 - #{l : d[i][l] > d[i][j] and d_j[l] > d[i][j]} / c
+__global__ void __launch_bounds__(RS_WARPS * 32)
+mp_empiric_kernel(const double *__restrict__ dist, const int64_t *__restrict__ ind, int64_t n, int c,
+                  const double *__restrict__ rev_dist, const int64_t *__restrict__ rev_ind, int64_t m,
+                  int c_rev, int P, int k, double *__restrict__ out_dist,
+                  int64_t *__restrict__ out_ind) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * RS_WARPS + warp;
+    if (row >= n) return;
+    RowBuf b = row_buf(smem_raw, warp, P);
+    // extra per-warp scratch after the three RowBuf planes: d copy [P] + result [P]
+    double *dcopy = reinterpret_cast<double *>(smem_raw) + (size_t)3 * RS_WARPS * P + (size_t)warp * 2 * P;
+    double *res = dcopy + P;
+    for (int j = lane; j < c; j += 32) {
+        dcopy[j] = dist[row * c + j];
+        b.pay[j] = ind[row * c + j];
+        b.tie[j] = j;
+    }
+    __syncwarp();
+    for (int j = 0; j < c; ++j) {
+        const int64_t cj = b.pay[j];
+        const double dij = dcopy[j];
+        int count = 0;
+        if (cj >= 0 && cj < m) {
+            const double *rd = rev_dist + cj * c_rev;
+            const int64_t *ri = rev_ind + cj * c_rev;
+            const double fill = rd[c_rev - 1] + 1e-6;
+            for (int l = lane; l < c; l += 32) {
+                const int64_t tl = b.pay[l];
+                double dj = fill;
+                for (int p = 0; p < c_rev; ++p)
+                    if (ri[p] == tl) dj = rd[p];
+                count += (dcopy[l] > dij) && (dj > dij);
+            }
+        }
+        count = __reduce_add_sync(FULL_MASK, count);
+        if (lane == 0) res[j] = 1.0 - (double)count / (double)c;
+    }
+    __syncwarp();
+    for (int j = lane; j < c; j += 32) b.key[j] = res[j];
+    emit_row(b, c, P, k, row, lane, out_dist, out_ind);
+}
+
+// DisSimLocal._fit: centroid of the reverse neighbours + squared distance to it.
+// One warp per target row; lanes stride over features, fp64 accumulation.
+template <typename T>
+__global__ void __launch_bounds__(RS_WARPS * 32)
+dsl_fit_kernel(const T *__restrict__ source, int64_t n_source, int64_t lds,
+               const T *__restrict__ target, int64_t m, int64_t ldt, int d,
+               const int64_t *__restrict__ rev_ind, int c_rev, double *__restrict__ centroids,
+               double *__restrict__ dist_to_cent) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * RS_WARPS + warp;
+    if (row >= m) return;
+    const int64_t *ri = rev_ind + row * c_rev;
+    double acc2 = 0.0;
+    for (int t = lane; t < d; t += 32) {
+        double s = 0.0;
+        for (int p = 0; p < c_rev; ++p) {
+            const int64_t id = ri[p];
+            s += (id >= 0 && id < n_source) ? (double)source[id * lds + t] : 0.0;
+        }
+        const double cen = s / (double)c_rev;
+        if (centroids) centroids[row * d + t] = cen;
+        const double e = (double)target[row * ldt + t] - cen;
+        acc2 += e * e;
+    }
+    acc2 = warp_sum(acc2);
+    if (lane == 0) dist_to_cent[row] = acc2;
+}
+
+__device__ __forceinline__ void atomic_min_double(double *addr, double v) {
+    unsigned long long *a = reinterpret_cast<unsigned long long *>(addr);
+    unsigned long long old = *a;
+    while (v < __longlong_as_double((long long)old)) {
+        const unsigned long long assumed = old;
+        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+        if (old == assumed) break;
+    }
+}
+
+// DisSimLocal.transform stage 1.  The oracle computes ||q-t||^2 in the expanded
+// form clamped at 0 (sklearn euclidean_distances); the direct fp64 difference
+// used here is the same number to ~1e-13 relative and never negative.
+// One warp per query row; lane l owns features l, l+32, ... (U per 32*U-wide
+// chunk, in registers) so every candidate row is read once, coalesced, and feeds
+// both the pairwise distance and the local centroid.
+template <typename T, int U>
+__global__ void __launch_bounds__(RS_WARPS * 32)
+dsl_transform_kernel(const T *__restrict__ query, int64_t n, int64_t ldq,
+                     const T *__restrict__ target, int64_t m, int64_t ldt, int d,
+                     const int64_t *__restrict__ ind, int c, const double *__restrict__ dist_to_cent,
+                     double *__restrict__ raw, double *__restrict__ global_min) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * RS_WARPS + warp;
+    if (row >= n) return;
+    double *sq = reinterpret_cast<double *>(smem_raw) + (size_t)warp * c;   // [c] per warp
+    const T *qr = query + row * ldq;
+    const int64_t *ir = ind + row * c;
+    for (int j = lane; j < c; j += 32) sq[j] = 0.0;
+    __syncwarp();
+    double qc2 = 0.0;   // ||q - centroid||^2, this lane's features
+    for (int f0 = 0; f0 < d; f0 += 32 * U) {
+        T qv[U];
+        double csum[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int t = f0 + lane + 32 * u;
+            qv[u] = (t < d) ? qr[t] : T(0);
+            csum[u] = 0.0;
+        }
+        for (int j = 0; j < c; ++j) {
+            const int64_t id = ir[j];
+            const bool ok = id >= 0 && id < m;
+            const T *tr = target + (ok ? id : 0) * ldt;
+            double part = 0.0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int t = f0 + lane + 32 * u;
+                const T tv = (ok && t < d) ? tr[t] : T(0);
+                csum[u] += (double)tv;
+                const double e = (double)qv[u] - (double)tv;
+                part += e * e;
+            }
+            part = warp_sum(part);
+            if (lane == 0) sq[j] += part;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int t = f0 + lane + 32 * u;
+            if (t < d) {
+                const double e = (double)qv[u] - csum[u] / (double)c;
+                qc2 += e * e;
+            }
+        }
+    }
+    qc2 = warp_sum(qc2);
+    __syncwarp();
+    double mn = INFINITY;
+    for (int j = lane; j < c; j += 32) {
+        const int64_t id = ir[j];
+        const double dc = (id >= 0 && id < m) ? dist_to_cent[id] : 0.0;
+        const double v = sq[j] - qc2 - dc;
+        raw[row * c + j] = v;
+        mn = fmin(mn, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mn = fmin(mn, __shfl_xor_sync(FULL_MASK, mn, o));
+    if (lane == 0) atomic_min_double(global_min, mn);
+}
+
+__global__ void __launch_bounds__(RS_WARPS * 32)
+dsl_finish_kernel(const double *__restrict__ raw, const int64_t *__restrict__ ind, int64_t n, int c,
+                  const double *__restrict__ global_min, int squared, int P, int k,
+                  double *__restrict__ out_dist, int64_t *__restrict__ out_ind) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * RS_WARPS + warp;
+    if (row >= n) return;
+    RowBuf b = row_buf(smem_raw, warp, P);
+    const double mn = *global_min;
+    const double shift = (mn < 0.0) ? -mn : 0.0;
+    for (int j = lane; j < c; j += 32) {
+        double v = raw[row * c + j] + shift;
+        if (!squared) v = sqrt(v);
+        b.key[j] = v;
+        b.pay[j] = ind[row * c + j];
+        b.tie[j] = j;
+    }
+    emit_row(b, c, P, k, row, lane, out_dist, out_ind);
+}
+
+}  // namespace kb2
+
+using namespace kb2;
+
+#define RS_GRID(n) (unsigned)ceil_div64((n), RS_WARPS), RS_WARPS * 32
+
+extern "C" int kb2_row_stats(const double *dist, int64_t n, int c, double *mean, double *sd,
+                             double *last, void *stream) {
+    KB2_CHECK(n >= 0 && c > 0, "row_stats: bad shape");
+    if (n == 0) return 0;
+    row_stats_kernel<<<RS_GRID(n), 0, (cudaStream_t)stream>>>(dist, n, c, mean, sd, last);
+    KB2_LAUNCH_CHECK();
+    return 0;
+}
+
+static int check_row_args(const char *what, int64_t n, int c, int k) {
+    KB2_CHECK(n >= 0 && c > 0 && c <= 2048, "%s: c=%d outside (0, 2048]", what, c);
+    KB2_CHECK(k >= 0 && k <= c, "%s: k=%d must be in [0, c=%d]", what, k, c);
+    return 0;
+}
+
+extern "C" int kb2_rescale_topk(int mode, const double *dist, const int64_t *ind, int64_t n, int c,
+                                const double *stat_a, const double *stat_b, int64_t n_stats, int k,
+                                double *out_dist, int64_t *out_ind, void *stream) {
+    if (check_row_args("rescale_topk", n, c, k)) return 1;
+    KB2_CHECK(mode >= 0 && mode <= 3, "rescale_topk: unknown mode %d", mode);
+    KB2_CHECK(stat_a != nullptr && (mode != KB2_RESCALE_MP_GAUSS || stat_b != nullptr),
+              "rescale_topk: missing per-target statistics");
+    if (n == 0) return 0;
+    const int P = next_pow2(c);
+    const size_t smem = (size_t)RS_WARPS * P * 24;
+    KB2_CUDA(cudaFuncSetAttribute(rescale_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    rescale_topk_kernel<<<RS_GRID(n), smem, (cudaStream_t)stream>>>(
+        mode, dist, ind, n, c, stat_a, stat_b, n_stats, P, k, out_dist, out_ind);
+    KB2_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int kb2_mp_empiric_topk(const double *dist, const int64_t *ind, int64_t n, int c,
+                                   const double *rev_dist, const int64_t *rev_ind, int64_t m,
+                                   int c_rev, int k, double *out_dist, int64_t *out_ind,
+                                   void *stream) {
+    if (check_row_args("mp_empiric_topk", n, c, k)) return 1;
+    KB2_CHECK(m > 0 && c_rev > 0, "mp_empiric_topk: bad reverse shape");
+    if (n == 0) return 0;
+    const int P = next_pow2(c);
+    const size_t smem = (size_t)RS_WARPS * P * (24 + 16);
+    KB2_CUDA(cudaFuncSetAttribute(mp_empiric_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    mp_empiric_kernel<<<RS_GRID(n), smem, (cudaStream_t)stream>>>(
+        dist, ind, n, c, rev_dist, rev_ind, m, c_rev, P, k, out_dist, out_ind);
+    KB2_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int kb2_dsl_fit(const void *source, int64_t n_source, int64_t lds, const void *target,
+                           int64_t m, int64_t ldt, int d, int elem_size, const int64_t *rev_ind,
+                           int c_rev, double *centroids, double *dist_to_cent, void *stream) {
+    KB2_CHECK(m >= 0 && d > 0 && c_rev > 0 && lds >= d && ldt >= d, "dsl_fit: bad shape");
+    KB2_CHECK(elem_size == 4 || elem_size == 8, "dsl_fit: elem_size must be 4 or 8");
+    if (m == 0) return 0;
+    if (elem_size == 4)
+        dsl_fit_kernel<float><<<RS_GRID(m), 0, (cudaStream_t)stream>>>(
+            (const float *)source, n_source, lds, (const float *)target, m, ldt, d, rev_ind, c_rev,
+            centroids, dist_to_cent);
+    else
+        dsl_fit_kernel<double><<<RS_GRID(m), 0, (cudaStream_t)stream>>>(
+            (const double *)source, n_source, lds, (const double *)target, m, ldt, d, rev_ind, c_rev,
+            centroids, dist_to_cent);
+    KB2_LAUNCH_CHECK();
+    return 0;
+}
+
+template <typename T>
+static int launch_dsl_transform(const void *query, int64_t n, int64_t ldq, const void *target,
+                                int64_t m, int64_t ldt, int d, const int64_t *ind, int c,
+                                const double *dist_to_cent, double *raw, double *global_min,
+                                cudaStream_t st) {
+    const size_t smem = (size_t)RS_WARPS * c * sizeof(double);
+    if (d <= 128)
+        dsl_transform_kernel<T, 4><<<RS_GRID(n), smem, st>>>((const T *)query, n, ldq, (const T *)target,
+                                                            m, ldt, d, ind, c, dist_to_cent, raw,
+                                                            global_min);
+    else
+        dsl_transform_kernel<T, 8><<<RS_GRID(n), smem, st>>>((const T *)query, n, ldq, (const T *)target,
+                                                            m, ldt, d, ind, c, dist_to_cent, raw,
+                                                            global_min);
+    KB2_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int kb2_dsl_transform(const void *query, int64_t n, int64_t ldq, const void *target,
+                                 int64_t m, int64_t ldt, int d, int elem_size, const int64_t *ind,
+                                 int c, const double *dist_to_cent, double *raw, double *global_min,
+                                 void *stream) {
+    KB2_CHECK(n >= 0 && d > 0 && c > 0 && c <= 2048 && ldq >= d && ldt >= d, "dsl_transform: bad shape");
+    KB2_CHECK(elem_size == 4 || elem_size == 8, "dsl_transform: elem_size must be 4 or 8");
+    if (n == 0) return 0;
+    if (elem_size == 4)
+        return launch_dsl_transform<float>(query, n, ldq, target, m, ldt, d, ind, c, dist_to_cent, raw,
+                                           global_min, (cudaStream_t)stream);
+    return launch_dsl_transform<double>(query, n, ldq, target, m, ldt, d, ind, c, dist_to_cent, raw,
+                                        global_min, (cudaStream_t)stream);
+}
+
+extern "C" int kb2_dsl_finish_topk(const double *raw, const int64_t *ind, int64_t n, int c,
+                                   const double *global_min, int squared, int k, double *out_dist,
+                                   int64_t *out_ind, void *stream) {
+    if (check_row_args("dsl_finish_topk", n, c, k)) return 1;
+    if (n == 0) return 0;
+    const int P = next_pow2(c);
+    const size_t smem = (size_t)RS_WARPS * P * 24;
+    KB2_CUDA(cudaFuncSetAttribute(dsl_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    dsl_finish_kernel<<<RS_GRID(n), smem, (cudaStream_t)stream>>>(raw, ind, n, c, global_min, squared,
+                                                                P, k, out_dist, out_ind);
+    KB2_LAUNCH_CHECK();
+    return 0;
+}

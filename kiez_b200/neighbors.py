@@ -1,0 +1,344 @@
+"""Nearest-neighbour plugin API and the ``B200`` exact backend.
+
+Mirrors, name for name, the reference's plugin interface
+(kiez/neighbors/neighbor_algorithm_base.py:13-136): ``NNAlgorithm`` with
+``fit`` / ``kneighbors`` and the abstract ``_fit`` / ``_kneighbors`` /
+``valid_metrics``.  ``B200`` implements it with the CUDA library behind
+include/kiez_b200.h: *prepare* (3xTF32 operand split, "index build"),
+*candidate search* (tcgen05 tiles + fused top-c selection) and *exact finish*
+(fp64 distances of the candidates, sorted) -- what
+kiez/neighbors/exact/sklearn_nearest_neighbors.py:83-101 delegates to
+scikit-learn's brute-force ``NearestNeighbors``.
+
+All backend logic lives in ``B200Mixin`` so that ``kiez_b200.plugin`` can also
+graft it onto the *real* ``kiez.neighbors.NNAlgorithm`` when kiez is installed.
+"""
+from __future__ import annotations
+
+import warnings
+from abc import ABC, abstractmethod
+from typing import Any, Optional, Tuple
+
+import numpy as np
+
+try:  # torch is plumbing here: device memory, streams, torch.distributed
+    import torch
+except ImportError:  # pragma: no cover
+    torch = None
+
+
+class NotFittedError(ValueError, AttributeError):
+    """Same bases as sklearn.exceptions.NotFittedError, which the reference raises."""
+
+
+def check_is_fitted(obj, attributes, all_or_any=all):
+    if not isinstance(attributes, (list, tuple)):
+        attributes = [attributes]
+    if not all_or_any([hasattr(obj, a) for a in attributes]):
+        raise NotFittedError(
+            f"This {type(obj).__name__} instance is not fitted yet. Call 'fit' with "
+            "appropriate arguments before using this estimator."
+        )
+
+
+class NNAlgorithm(ABC):
+    """Base class of nearest-neighbour backends (neighbor_algorithm_base.py:13)."""
+
+    _ALLOWED_INPUT_TYPES: Tuple[Any, ...] = (np.ndarray,)
+
+    def __init__(self, n_candidates, metric, n_jobs):
+        self.n_candidates = n_candidates
+        self.metric = metric
+        self.n_jobs = n_jobs
+
+    def _describe_source_target_fitted(self):
+        if hasattr(self, "source_"):
+            return (f" is fitted with: source.shape={self.source_.shape} and"
+                    f" target.shape={self.target_.shape}")
+        return " is unfitted"
+
+    @property
+    @abstractmethod
+    def valid_metrics(self):
+        ...
+
+    @abstractmethod
+    def _fit(self, data, is_source: bool) -> Any:
+        ...
+
+    @abstractmethod
+    def _kneighbors(self, k, query, index, return_distance, is_self_querying):
+        ...
+
+    def _check_input_types(self, value):
+        if not isinstance(value, tuple):
+            value = (value,)
+        allowed = self.__class__._ALLOWED_INPUT_TYPES
+        if any(x is not None and not isinstance(x, allowed) for x in value):
+            raise ValueError(
+                f"Not implemented for input type(s) {[type(x) for x in value]}! "
+                f"Only {allowed} allowed!"
+            )
+
+    def fit(self, source, target=None, only_fit_target: bool = False):
+        """Index the data (neighbor_algorithm_base.py:53-96)."""
+        self._check_input_types((source, target))
+        self.source_equals_target = target is None
+        if self.source_equals_target:
+            self.source_index = self._fit(source, True)
+            self.target_index = self.source_index
+            target = source
+        else:
+            if source.shape[1] != target.shape[1]:
+                raise ValueError(
+                    "Expected source and target to have the same number of features,"
+                    f" but got source.shape: {source.shape} and target.shape: {target.shape}"
+                )
+            if only_fit_target:
+                self.target_index = self._fit(target, True)
+            else:
+                self.source_index = self._fit(source, True)
+                self.target_index = self._fit(target, False)
+        self.source_ = source
+        self.target_ = target
+
+    def _check_k_value(self, k: int, needed_space) -> int:
+        if not np.issubdtype(type(k), np.integer):
+            raise TypeError(f"k does not take {type(k)} value, enter integer value")
+        if k <= 0:
+            raise ValueError(f"Expected k > 0. Got {k}")
+        if k > needed_space:
+            warnings.warn(
+                f"k={k} is larger than number of samples in indexed space.\n"
+                f"Setting to k={needed_space}",
+                stacklevel=2,
+            )
+            return needed_space
+        return k
+
+    def kneighbors(self, k=None, query=None, s_to_t=True, return_distance=True):
+        """neighbor_algorithm_base.py:116-136."""
+        check_is_fitted(self, ["source_index", "target_index"], all_or_any=any)
+        k = self.n_candidates if k is None else k
+        is_self_querying = query is None and self.source_equals_target
+        if s_to_t:
+            query = self.source_ if query is None else query
+            index = self.target_index
+            needed_space = self.target_.shape[0]
+        else:
+            query = self.target_ if query is None else query
+            index = self.source_index
+            needed_space = self.source_.shape[0]
+        k = self._check_k_value(k, needed_space)
+        return self._kneighbors(k=k, query=query, index=index,
+                                return_distance=return_distance,
+                                is_self_querying=is_self_querying)
+
+
+# ---------------------------------------------------------------------------
+# the B200 backend
+# ---------------------------------------------------------------------------
+
+_METRIC_CODES = {
+    "euclidean": 0, "l2": 0, "minkowski": 0,
+    "sqeuclidean": 1,
+    "cosine": 2,
+}
+
+
+class PreparedRows:
+    """Device-resident operands of one embedding matrix: the raw fp32 rows (exact
+    finish), their 3xTF32 split and selection term (candidate search)."""
+
+    __slots__ = ("raw", "hi", "lo", "key", "sqnorm", "n", "d", "dpad", "base", "_owner")
+
+    def __init__(self, raw, hi, lo, key, sqnorm, base=0, owner=None):
+        self.raw, self.hi, self.lo, self.key, self.sqnorm = raw, hi, lo, key, sqnorm
+        self.n, self.d = raw.shape
+        self.dpad = hi.shape[1]
+        self.base = base        # global id of row 0 (multi-GPU shards)
+        self._owner = owner     # keeps the user's array alive while its id() is a cache key
+
+    def rows(self, lo, hi):
+        """A contiguous row shard (views, no copy)."""
+        return PreparedRows(self.raw[lo:hi], self.hi[lo:hi], self.lo[lo:hi], self.key[lo:hi],
+                            None if self.sqnorm is None else self.sqnorm[lo:hi],
+                            base=self.base + lo, owner=self._owner)
+
+
+def candidate_capacity(c: int) -> int:
+    """Length of the per-row candidate list the search kernel keeps for `c` wanted
+    neighbours: a margin absorbs rank swaps between the fp32 3xTF32 selection key
+    and the exact fp64 distance at the c-th / (c+1)-th boundary."""
+    return min(128, ((c + max(6, c // 8)) + 7) // 8 * 8)
+
+
+class B200Mixin:
+    """Implementation of the exact B200 backend; combine with an NNAlgorithm base."""
+
+    valid_metrics = tuple(_METRIC_CODES)
+
+    def __init__(self, n_candidates: int = 5, metric: str = "euclidean", p: int = 2,
+                 device: Optional[Any] = None, impl: str = "auto", center: bool = True,
+                 distributed: Optional[bool] = None, n_jobs=None):
+        if torch is None or not torch.cuda.is_available():
+            raise ImportError(
+                "The B200 backend needs PyTorch with a CUDA device (sm_100a); there is no "
+                "CPU fallback."
+            )
+        from . import _lib  # raises ImportError when the CUDA library is not built
+
+        if metric not in self.__class__.valid_metrics:
+            raise ValueError(f"Unknown metric {metric}, please use one of {self.valid_metrics}")
+        if metric == "minkowski" and p != 2:
+            raise ValueError("B200 is an exact contraction backend: minkowski needs p=2")
+        if impl not in ("auto", "tc", "simt"):
+            raise ValueError(f"impl must be 'auto', 'tc' or 'simt', got {impl!r}")
+        super().__init__(n_candidates=n_candidates, metric=metric, n_jobs=n_jobs)
+        self.p = p
+        self.impl = impl
+        self.center = center
+        self._lib = _lib
+        self._metric_code = _METRIC_CODES[metric]
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
+            else torch.device(device)
+        if distributed is None:
+            distributed = torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1
+        self.distributed = bool(distributed)
+        self._prepared = {}
+        self._center_vec = None
+        self._input_is_numpy = False
+
+    def __repr__(self):
+        return (f"{self.__class__.__name__}(n_candidates={self.n_candidates},"
+                f"metric={self.metric},impl={self.impl},device={self.device},"
+                f"distributed={self.distributed})")
+
+    # -- NNAlgorithm hooks ---------------------------------------------------
+    def fit(self, source, target=None, only_fit_target: bool = False):
+        self._prepared = {}
+        self._center_vec = None
+        self._input_is_numpy = isinstance(source, np.ndarray)
+        return super().fit(source, target, only_fit_target=only_fit_target)
+
+    def _fit(self, data, is_source: bool):
+        return self._prepare(data, cache=True)
+
+    def _kneighbors(self, k, query, index, return_distance, is_self_querying):
+        q = self._prepare(query, cache=False)
+        if is_self_querying and k > index.n - 1:
+            # sklearn raises for n_neighbors > n_samples_fit - 1 with X=None
+            raise ValueError(
+                f"Expected n_neighbors <= n_samples_fit - 1, but n_neighbors = {k}, "
+                f"n_samples_fit = {index.n}"
+            )
+        if self.distributed:
+            from .distributed import sharded_knn
+
+            dist, ind = sharded_knn(self, q, index, k, is_self_querying)
+        else:
+            dist, ind = self.search(q, index, k, exclude_self=is_self_querying)
+        return (dist, ind) if return_distance else ind
+
+    # -- device pipeline -------------------------------------------------------
+    def to_device(self, data):
+        """C-contiguous rows on this backend's device: fp32 (the production dtype), or
+        float64 when the caller passes float64 (the README example does), in which case
+        the candidate search still runs on the fp32-rounded split but the exact finish
+        reads the caller's float64 values."""
+        if isinstance(data, np.ndarray):
+            keep64 = data.dtype == np.float64
+            t = torch.from_numpy(np.ascontiguousarray(
+                data, dtype=np.float64 if keep64 else np.float32))
+            return t.to(self.device, non_blocking=True)
+        keep64 = data.dtype == torch.float64
+        return data.to(device=self.device,
+                       dtype=torch.float64 if keep64 else torch.float32).contiguous()
+
+    def _prepare(self, data, cache: bool) -> PreparedRows:
+        hit = self._prepared.get(id(data))
+        if hit is not None:
+            return hit
+        lib = self._lib
+        raw = self.to_device(data)
+        if raw.dim() != 2:
+            raise ValueError(f"Expected a 2-d embedding matrix, got shape {tuple(raw.shape)}")
+        n, d = raw.shape
+        cosine = self._metric_code == lib.METRIC_COSINE
+        if self._center_vec is None and self.center and not cosine and n > 0:
+            # distances are translation invariant; centring keeps ||y||^2 - 2 q.y well
+            # conditioned in fp32 for embeddings far from the origin
+            self._center_vec = raw.mean(dim=0).to(torch.float32).contiguous()
+        dpad = lib.lib.kb2_padded_dim(d)
+        raw32 = raw if raw.dtype == torch.float32 else raw.to(torch.float32)
+        with torch.cuda.device(self.device):
+            hi = torch.empty((n, dpad), dtype=torch.float32, device=self.device)
+            lo = torch.empty((n, dpad), dtype=torch.float32, device=self.device)
+            key = torch.empty((n,), dtype=torch.float32, device=self.device)
+            sqn = torch.empty((n,), dtype=torch.float64, device=self.device) if cosine else None
+            if n:
+                lib.call("kb2_prepare_rows", lib.ptr(raw32), n, d, raw32.stride(0),
+                         None if cosine else lib.ptr(self._center_vec), self._metric_code,
+                         lib.ptr(hi), lib.ptr(lo), dpad, lib.ptr(key), lib.ptr(sqn),
+                         lib.stream_ptr())
+                if cosine and raw.dtype == torch.float64:
+                    sqn = (raw * raw).sum(dim=1)      # exact norms of the float64 rows
+        prep = PreparedRows(raw, hi, lo, key, sqn, owner=data)
+        if cache:
+            self._prepared[id(data)] = prep
+        return prep
+
+    def search(self, q: PreparedRows, y: PreparedRows, k: int, exclude_self: bool = False,
+               splits: Optional[int] = None):
+        """k nearest rows of `y` for every row of `q`: (dist float64, ind int64) on device,
+        rows ascending, ids global (y.base added)."""
+        lib = self._lib
+        if q.d != y.d:
+            raise ValueError(f"query has {q.d} features, index has {y.d}")
+        dev = self.device
+        with torch.cuda.device(dev):
+            out_d = torch.empty((q.n, k), dtype=torch.float64, device=dev)
+            out_i = torch.empty((q.n, k), dtype=torch.int64, device=dev)
+            if q.n == 0:
+                return out_d, out_i
+            cap = min(candidate_capacity(k), lib.lib.kb2_max_candidates())
+            if k > cap:
+                raise ValueError(
+                    f"B200 supports at most {lib.lib.kb2_max_candidates()} neighbours per "
+                    f"query and shard, got {k}")
+            if splits is None:
+                sm = torch.cuda.get_device_properties(dev).multi_processor_count
+                splits = lib.lib.kb2_suggest_splits(q.n, y.n, cap, sm)
+            ncand = splits * cap
+            cand = torch.empty((q.n, ncand), dtype=torch.int32, device=dev)
+            impl = {"auto": lib.KNN_AUTO, "tc": lib.KNN_TC, "simt": lib.KNN_SIMT}[self.impl]
+            st = lib.stream_ptr()
+            # exclude column j where j + self_offset == row  (ids local to q / y)
+            self_offset = y.base - q.base
+            lib.call("kb2_knn_candidates", impl, lib.ptr(q.hi), lib.ptr(q.lo), q.n,
+                     lib.ptr(y.hi), lib.ptr(y.lo), lib.ptr(y.key), y.n, q.dpad, cap, splits,
+                     int(exclude_self), self_offset, lib.ptr(cand), None, st)
+            q_raw, y_raw = q.raw, y.raw
+            if q_raw.dtype != y_raw.dtype:
+                q_raw, y_raw = q_raw.to(torch.float64), y_raw.to(torch.float64)
+            # fewer than k valid candidates (a shard smaller than k) come back as +inf / -1
+            lib.call("kb2_refine_topk", lib.ptr(q_raw), q.n, q_raw.stride(0), lib.ptr(y_raw),
+                     y.n, y_raw.stride(0), q.d, q_raw.element_size(), lib.ptr(q.sqnorm),
+                     lib.ptr(y.sqnorm),
+                     lib.ptr(cand), ncand, self._metric_code, y.base, k,
+                     lib.ptr(out_d), lib.ptr(out_i), st)
+        return out_d, out_i
+
+
+class B200(B200Mixin, NNAlgorithm):
+    """Exact kNN on one or more B200 GPUs; ``Kiez(algorithm="B200")``.
+
+    Parameters mirror SklearnNN where they apply (n_candidates, metric, p, n_jobs).
+    ``impl``: "auto"/"tc" = tcgen05 tensor-core search, "simt" = FP32-pipe cross-check.
+    ``distributed``: shard the index side over the ranks of an initialised
+    torch.distributed (NCCL) group; default: on when world_size > 1.
+    """
+
+    if torch is not None:
+        _ALLOWED_INPUT_TYPES = (np.ndarray, torch.Tensor)

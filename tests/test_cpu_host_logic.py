@@ -1,0 +1,147 @@
+"""not gpu: host-side mirror of the reference's plugin interface -- resolver names, argument
+validation, k clamping, error types (tests/test_kiez.py, tests/neighbors/test_neighbor_base.py,
+tests/hubness_reduction/test_wrong_inputs.py of the reference)."""
+import warnings
+
+import numpy as np
+import pytest
+
+from kiez_b200 import (CSLS, B200, DisSimLocal, Kiez, LocalScaling, MutualProximity,
+                       NNAlgorithm, NoHubnessReduction)
+from kiez_b200.distributed import shard_bounds
+from kiez_b200.kiez import hubness_reduction_resolver, nn_algorithm_resolver
+from kiez_b200.neighbors import NotFittedError, candidate_capacity
+from oracle import kiez_oracle as O
+
+
+class OracleNN(NNAlgorithm):
+    """CPU stand-in backend (oracle arithmetic) to drive the NNAlgorithm base class."""
+
+    valid_metrics = ("euclidean",)
+
+    def __init__(self, n_candidates=5, metric="euclidean", p=2):
+        super().__init__(n_candidates=n_candidates, metric=metric, n_jobs=None)
+        self.p = p
+
+    def _fit(self, data, is_source):
+        return np.asarray(data)
+
+    def _kneighbors(self, k, query, index, return_distance, is_self_querying):
+        d, i = O.knn_brute(query, index, k, exclude_self=is_self_querying)
+        return (d, i) if return_distance else i
+
+
+def test_resolver_names():
+    assert set(Kiez.show_hubness_options()) == {"mutualproximity", "dissimlocal", "localscaling",
+                                                "no", "csls"}        # tests/test_kiez.py:145-148
+    assert nn_algorithm_resolver.lookup("B200") is B200
+    assert nn_algorithm_resolver.lookup("b200") is B200
+    assert hubness_reduction_resolver.lookup("NoHubnessReduction") is NoHubnessReduction
+    assert hubness_reduction_resolver.lookup(None) is NoHubnessReduction
+    assert hubness_reduction_resolver.lookup("CSLS") is CSLS
+    assert hubness_reduction_resolver.lookup(LocalScaling) is LocalScaling
+    with pytest.raises(KeyError):
+        hubness_reduction_resolver.lookup("nope")
+    inst = OracleNN()
+    assert nn_algorithm_resolver.make(inst, {"n_candidates": 3}) is inst      # instance as-is
+
+
+def test_b200_needs_cuda_and_fails_loudly():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(ImportError, match="no CPU fallback"):
+        B200()
+    with pytest.raises(ImportError):
+        Kiez(algorithm="B200")
+    assert Kiez.show_algorithm_options() == []
+
+
+def test_kiez_argument_validation():
+    with pytest.raises(ValueError, match="Expected"):
+        Kiez(n_candidates=-1, algorithm=OracleNN())                  # tests/test_kiez.py:89-91
+    with pytest.raises(TypeError, match="does not"):
+        Kiez(n_candidates="1", algorithm=OracleNN())                 # :94-96
+    for hub, kw in [(None, {}), ("CSLS", {}), ("MutualProximity", {"method": "empiric"}),
+                    ("LocalScaling", {"method": "nicdm"}), ("DisSimLocal", {})]:
+        with pytest.raises(ValueError, match="Cannot"):              # :80-86
+            Kiez(algorithm=OracleNN(n_candidates=1), hubness=hub, hubness_kwargs=dict(kw))
+    with pytest.raises(ValueError, match="only supports"):
+        Kiez(algorithm=OracleNN(p=1, metric="minkowski"), hubness="DisSimLocal")   # :99-101
+    with pytest.raises(ValueError, match="only supports"):
+        Kiez(algorithm=OracleNN(metric="cosine"), hubness="DisSimLocal")           # :104-106
+    assert Kiez(algorithm=OracleNN(metric="sqeuclidean"), hubness="DisSimLocal").hubness.squared
+    assert not Kiez(algorithm=OracleNN(), hubness="DisSimLocal",
+                    hubness_kwargs={"squared": True}).hubness.squared       # dis_sim.py:47-54
+    with pytest.raises(ValueError, match="not recognized"):
+        MutualProximity(method="wrong", nn_algo=OracleNN())          # test_wrong_inputs.py
+    with pytest.raises(ValueError, match="Invalid method"):
+        LocalScaling(method="wrong", nn_algo=OracleNN())
+    assert LocalScaling(method="NICDM", nn_algo=OracleNN()).method == "nicdm"
+    assert MutualProximity(method="gaussi", nn_algo=OracleNN()).method == "normal"
+    assert MutualProximity(method="exact", nn_algo=OracleNN()).method == "empiric"
+
+
+def test_nn_base_fit_and_k_checks():
+    rng = np.random.RandomState(42)
+    source, target = rng.rand(20, 5), rng.rand(50, 5)
+    algo = OracleNN(n_candidates=5)
+    assert "unfitted" in algo._describe_source_target_fitted()
+    with pytest.raises(NotFittedError):
+        algo.kneighbors()
+    with pytest.raises(ValueError, match="Not implemented for input type"):
+        algo.fit([[1.0]], target)
+    with pytest.raises(ValueError, match="same number of features"):
+        algo.fit(source, rng.rand(10, 4))
+    algo.fit(source, target)
+    assert "source.shape=(20, 5)" in algo._describe_source_target_fitted()
+    with pytest.raises(TypeError, match="does not take"):            # test_neighbor_base.py:21-30
+        algo._check_k_value(k="test", needed_space=2)
+    with pytest.raises(ValueError, match="Expected"):
+        algo._check_k_value(k=0, needed_space=2)
+    with pytest.warns(UserWarning, match="larger than number of samples"):
+        assert algo._check_k_value(k=3, needed_space=2) == 2
+    d, i = algo.kneighbors()
+    assert i.shape == (20, 5)
+    d, i = algo.kneighbors(k=3, query=target, s_to_t=False)
+    assert i.shape == (50, 3) and i.max() < 20
+    # only_fit_target builds no source index (tests/test_kiez.py:22-28)
+    algo2 = OracleNN()
+    algo2.fit(source, target, only_fit_target=True)
+    assert not hasattr(algo2, "source_index")
+    # single-source mode: self is excluded only when query is None
+    algo3 = OracleNN(n_candidates=3)
+    algo3.fit(source)
+    _, i = algo3.kneighbors()
+    assert not (i == np.arange(20)[:, None]).any()
+    _, i = algo3.kneighbors(query=source, s_to_t=False)
+    assert (i[:, 0] == np.arange(20)).all()
+
+
+def test_set_k_if_needed_warnings():
+    hub = CSLS(nn_algo=OracleNN(n_candidates=5))
+    with pytest.warns(UserWarning, match="No k supplied"):
+        assert hub._set_k_if_needed(None) == 5
+    with pytest.warns(UserWarning, match="k > n_candidates"):
+        assert hub._set_k_if_needed(20) == 5
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        assert hub._set_k_if_needed(3) == 3
+    assert "CSLS" in repr(hub) and "DisSimLocal(squared = False)" == repr(
+        DisSimLocal(nn_algo=OracleNN()))
+
+
+def test_candidate_capacity_and_shard_bounds():
+    for c in range(1, 129):
+        cap = candidate_capacity(c)
+        assert cap <= 128 and cap % 8 == 0 and cap >= min(c, 128)
+        if c <= 110:
+            assert cap >= c + 6
+    for n in (0, 1, 7, 8, 9, 1000003):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
