@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""Benchmark of the kiez hot path on B200: queries/s of exact kNN + hubness reduction.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c2|c3|c5|custom ...]
+    python bench.py --impl reference ...      # the reference's CPU path, bounded sample
+
+One *step* = one full ``Kiez(algorithm=B200, hubness=CSLS).fit(source, target)`` +
+``kneighbors(k)`` (+ ``hubness_score``) over the whole synthetic workload, i.e. both kNN
+passes, the rescale and the final sort for every query.  Default workload = BASELINE.json's
+metric config (C4: 1M x 1M, d=256, CSLS, k=10).  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+WORKLOADS = {
+    # name: n (source rows), m (target rows), d, n_candidates, k, hubness
+    "c1": dict(n=100, m=100, d=50, c=10, k=5, hubness="CSLS"),
+    "c2": dict(n=15_000, m=15_000, d=256, c=50, k=10, hubness="CSLS"),
+    "c3": dict(n=100_000, m=100_000, d=256, c=100, k=10, hubness="MutualProximity"),
+    "c4": dict(n=1_000_000, m=1_000_000, d=256, c=10, k=10, hubness="CSLS"),
+    "c5": dict(n=1_000_000, m=10_000_000, d=128, c=50, k=10, hubness="LocalScaling"),
+}
+HUB_KWARGS = {"LocalScaling": {"method": "nicdm"}, "MutualProximity": {"method": "normal"}}
+ORACLE_HUB = {"CSLS": "csls", "LocalScaling": "nicdm", "MutualProximity": "mp_gaussian",
+              "DisSimLocal": "dsl", None: "no"}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c4", choices=list(WORKLOADS) + ["custom"])
+    ap.add_argument("--n", type=int)
+    ap.add_argument("--m", type=int)
+    ap.add_argument("--d", type=int)
+    ap.add_argument("--c", type=int)
+    ap.add_argument("--k", type=int)
+    ap.add_argument("--hubness", default=None)
+    ap.add_argument("--search-impl", default="auto", choices=["auto", "tc", "simt"])
+    ap.add_argument("--no-hub-scores", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="rows per direction for the CPU leg")
+    return ap.parse_args()
+
+
+def workload(args):
+    w = dict(WORKLOADS["c4" if args.workload == "custom" else args.workload])
+    for key in ("n", "m", "d", "c", "k"):
+        if getattr(args, key) is not None:
+            w[key] = getattr(args, key)
+    if args.hubness is not None:
+        w["hubness"] = None if args.hubness.lower() in ("none", "no") else args.hubness
+    w["name"] = (f"{args.workload}: {w['n']}x{w['m']} d={w['d']} fp32 gaussian, exact kNN "
+                 f"c={w['c']} + {w['hubness']} k={w['k']}")
+    return w
+
+
+def synth(n, d, seed, device):
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    return torch.randn((n, d), generator=g, device=device, dtype=torch.float32)
+
+
+# ---------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md "clocks line")
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._thr = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                     "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+                for nm, v in zip(names, s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# CPU leg: the reference's SklearnNN + numpy hubness path (oracle port), bounded sample
+# ---------------------------------------------------------------------------
+def cpu_reference_step(w, sample, source, target):
+    """Forward: `sample` source rows vs the full target index; reverse: `sample` target rows vs
+    the full source index; rescale + sort on the slice.  Brute-force cost per query is
+    independent of the other queries, so queries/s extrapolates linearly."""
+    from oracle import kiez_oracle as O
+
+    c, k = w["c"], w["k"]
+    t0 = time.perf_counter()
+    fwd_d, fwd_i = O.knn_sklearn(source[:sample], target, min(c, target.shape[0]), n_jobs=-1)
+    rev_d, _ = O.knn_sklearn(target[:sample], source, min(c, source.shape[0]), n_jobs=-1)
+    # the rescale needs reverse statistics of the gathered targets: on the slice we take the
+    # statistics of the sampled reverse rows (same arithmetic volume per query as the full run)
+    stats_idx = fwd_i % rev_d.shape[0]
+    hub = ORACLE_HUB[w["hubness"]]
+    if hub == "csls":
+        out = O.csls_transform(fwd_d, stats_idx, rev_d)
+    elif hub == "nicdm":
+        out = O.local_scaling_transform(fwd_d, stats_idx, rev_d, "nicdm")
+    elif hub == "mp_gaussian":
+        out = O.mp_gaussian_transform(fwd_d, stats_idx, rev_d)
+    else:
+        out = fwd_d
+    O.sort_topk(out, fwd_i, k)
+    return time.perf_counter() - t0
+
+
+def cpu_sample_rows(w, requested):
+    if requested:
+        return min(requested, w["n"], w["m"])
+    # ~10-30 s of CPU work: 4 n m d flop per full step, assume >= 100 GFLOP/s sustained
+    per_query = 4.0 * max(w["n"], w["m"]) * w["d"]
+    rows = int(1.0e12 / per_query)
+    return int(max(64, min(rows, w["n"], w["m"], 8192)))
+
+
+def run_reference(args, w):
+    """--impl reference: the reference's own CPU implementation of the path on this box's host
+    cores.  /root/reference is not present on the GPU box, so this is the oracle port, which
+    performs the same scikit-learn call (NearestNeighbors brute, n_jobs=-1) + numpy rescale."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    rng = np.random.default_rng(0)
+    source = rng.standard_normal((w["n"], w["d"]), dtype=np.float32)
+    target = np.random.default_rng(1).standard_normal((w["m"], w["d"]), dtype=np.float32)
+    sample = cpu_sample_rows(w, args.cpu_sample)
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_step(w, min(sample, 256), source, target)
+    times = [cpu_reference_step(w, sample, source, target) for _ in range(max(1, args.steps))]
+    t = sum(times) / len(times)
+    value = sample / t
+    line = {
+        "impl": "reference", "metric": "queries_per_s", "value": value, "unit": "queries/s",
+        "n_gpus": args.gpus, "steps": len(times), "warmup": min(args.warmup, 1),
+        "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["name"]},
+        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} source rows vs all {w['m']} targets + {sample} target "
+                                   f"rows vs all {w['n']} sources + rescale, extrapolated linearly"},
+        "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"bf16_sustained": p.get("bf16_tflops_sustained"), "bf16_burst": p.get("bf16_tflops"),
+                "hbm_gbs": p.get("hbm_gbs"), "source": "MEASURED_PEAKS.json"}
+    return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+def tf32_cublas_tflops(device):
+    """cuBLAS TF32 GEMM rate measured live (MEASURED_PEAKS.json has no TF32 entry)."""
+    import torch
+
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn((8192, 8192), device=device)
+        b = torch.randn((8192, 8192), device=device)
+        for _ in range(3):
+            a @ b
+        best = 0.0
+        for _ in range(8):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            e1.synchronize()
+            best = max(best, 2 * 8192 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        return best
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def run_b200(args, w):
+    import torch
+    import torch.distributed as dist
+
+    from kiez_b200 import B200, Kiez, _lib, hubness_score
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    source = synth(w["n"], w["d"], 0, device)
+    target = synth(w["m"], w["d"], 1, device)
+    hub_kwargs = HUB_KWARGS.get(w["hubness"], {})
+
+    def make():
+        algo = B200(n_candidates=w["c"], metric="euclidean", impl=args.search_impl,
+                    distributed=world > 1)
+        return Kiez(n_candidates=w["c"], algorithm=algo, hubness=w["hubness"],
+                    hubness_kwargs=dict(hub_kwargs))
+
+    def step(src, tgt, profile=None):
+        inst = make()
+        inst.algorithm._profile = profile
+        inst.fit(src, tgt)
+        dist_, ind_ = inst.kneighbors(w["k"])
+        if not args.no_hub_scores:
+            scores = hubness_score(torch.as_tensor(ind_, device=device), w["m"], k=w["k"])
+        else:
+            scores = None
+        return dist_, ind_, scores
+
+    for _ in range(args.warmup):
+        step(source, target)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    profile = []
+    launches0 = _lib.launch_counter
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        out = step(source, target, profile)
+    ev1.record()
+    barrier()
+    launches = _lib.launch_counter - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = w["n"] / (ms_per_step * 1e-3)
+
+    # roofline of the dominant kernel (candidate search) from CUDA events around its launches
+    k_ms = [a.elapsed_time(b) for (a, b, *_r) in profile]
+    k_flop = [2.0 * nq * ny * d for (_a, _b, nq, ny, d) in profile]
+    peaks = measured_peaks()
+    tf32_peak = peaks["bf16_sustained"] / 2.0
+    achieved = (sum(k_flop) / (sum(k_ms) * 1e-3) / 1e12) if k_ms else 0.0
+    roofline = {
+        "bound": "tensor", "kernel": "knn_tc_kernel (3xTF32 tcgen05 + fused top-c)",
+        "achieved": achieved, "peak": tf32_peak / 3.0, "unit": "TFLOP/s",
+        "frac": achieved / (tf32_peak / 3.0), "traffic": None,
+        "issued_tf32_tflops": 3.0 * achieved, "tf32_peak": tf32_peak,
+        "peak_source": f"{peaks['source']} bf16_tflops_sustained / 2 (TF32 rate) / 3 (3xTF32 "
+                       "issues 3 MMAs per algorithmic MAC)",
+        "launches": len(k_ms), "avg_launch_ms": (sum(k_ms) / len(k_ms)) if k_ms else None,
+        "kernel_share_of_step": (sum(k_ms) / ms) if ms else None,
+        "algorithmic_flop_per_launch": (sum(k_flop) / len(k_flop)) if k_flop else None,
+    }
+    if rank == 0:
+        try:
+            roofline["tf32_cublas_tflops_live"] = tf32_cublas_tflops(device)
+        except Exception as exc:  # pragma: no cover
+            roofline["tf32_cublas_tflops_live"] = f"failed: {exc}"
+
+    # end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timing
+    e2e = None
+    if not args.no_e2e:
+        src_h = source.cpu().pin_memory().numpy()
+        tgt_h = target.cpu().pin_memory().numpy()
+        barrier()
+        n_e2e = max(1, min(args.steps, 2))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            d_, i_, _s = step(src_h, tgt_h)           # numpy in -> numpy out (D2H inside)
+        barrier()
+        t_e2e = (time.perf_counter() - t0) / n_e2e
+        if world > 1:
+            t = torch.tensor([t_e2e], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_e2e = float(t.item())
+        e2e = {"value": w["n"] / t_e2e, "unit": "queries/s",
+               "h2d_bytes_per_step": int(src_h.nbytes + tgt_h.nbytes),
+               "d2h_bytes_per_step": int(d_.nbytes + i_.nbytes), "steps": n_e2e,
+               "timer": "host wall clock around fit+kneighbors incl. copies, max over ranks"}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cores = len(os.sched_getaffinity(0))
+        sample = cpu_sample_rows(w, args.cpu_sample)
+        src_np, tgt_np = source.cpu().numpy(), target.cpu().numpy()
+        cpu_reference_step(w, min(sample, 256), src_np, tgt_np)
+        t_cpu = cpu_reference_step(w, sample, src_np, tgt_np)
+        cpu = {"value": sample / t_cpu, "unit": "queries/s", "cores": cores, "kind": "port",
+               "sample": f"{sample} source rows vs all {w['m']} targets + {sample} target rows vs "
+                         f"all {w['n']} sources + rescale ({t_cpu:.1f} s), extrapolated linearly"}
+
+    if rank == 0:
+        line = {
+            "metric": "queries_per_s", "value": value, "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "tf32x3",
+            "data": "synthetic",
+            "config": {"workload": w["name"], "l2": "inputs (>=1 GB) exceed the 126 MB L2",
+                       "search_impl": args.search_impl, "hub_scores": not args.no_hub_scores,
+                       "parallelism": f"index rows sharded over {world} GPU(s), NCCL all-gather + "
+                                      "merge kernel" if world > 1 else "single GPU"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": launches,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    w = workload(args)
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_b200(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -63,14 +63,16 @@ for _name, _args in SIGNATURES.items():
     _fn.restype = _int
     _fn.argtypes = _args
 
-#: number of kernel-launching C-ABI calls made through `call` (bench.py reports it)
+#: kernels each entry point launches (memsets not counted); bench.py reports the total
+KERNELS_PER_CALL = {"kb2_index_range": 2, "kb2_compact_ids": 3, "kb2_gini_numerator": 2}
+#: number of kiez_b200 kernels launched through `call` so far
 launch_counter = 0
 
 
 def call(name: str, *args) -> None:
     """Invoke a status-returning entry point; raise RuntimeError on failure."""
     global launch_counter
-    launch_counter += 1
+    launch_counter += KERNELS_PER_CALL.get(name, 1)
     status = getattr(lib, name)(*args)
     if status != 0:
         raise RuntimeError(f"{name} failed: {lib.kb2_last_error().decode()}")

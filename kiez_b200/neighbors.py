@@ -316,9 +316,17 @@ class B200Mixin:
             st = lib.stream_ptr()
             # exclude column j where j + self_offset == row  (ids local to q / y)
             self_offset = y.base - q.base
+            prof = getattr(self, "_profile", None)   # bench.py: CUDA events around the search
+            if prof is not None:
+                ev0 = torch.cuda.Event(enable_timing=True)
+                ev0.record()
             lib.call("kb2_knn_candidates", impl, lib.ptr(q.hi), lib.ptr(q.lo), q.n,
                      lib.ptr(y.hi), lib.ptr(y.lo), lib.ptr(y.key), y.n, q.dpad, cap, splits,
                      int(exclude_self), self_offset, lib.ptr(cand), None, st)
+            if prof is not None:
+                ev1 = torch.cuda.Event(enable_timing=True)
+                ev1.record()
+                prof.append((ev0, ev1, q.n, y.n, q.d))
             q_raw, y_raw = q.raw, y.raw
             if q_raw.dtype != y_raw.dtype:
                 q_raw, y_raw = q_raw.to(torch.float64), y_raw.to(torch.float64)

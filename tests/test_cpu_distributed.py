@@ -1,0 +1,85 @@
+"""not gpu: the N>1 path (shard -> per-shard top-k -> all-gather -> merge) with world_size=2
+over gloo on CPU.  The search and merge stages are injected (oracle arithmetic / numpy), so
+what is tested is the host logic the NCCL run shares: shard bounds, global ids, the
+self-exclusion offset, the packed gather layout and the merge order."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from kiez_b200.distributed import shard_bounds, sharded_topk
+from oracle import kiez_oracle as O
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _numpy_merge(g_dist, g_ind, nparts, part_stride, k, nq):
+    """Reference semantics of kb2_topk_rows(nparts>1): row r = concat over parts of
+    dist[p*part_stride + r*k .. +k), sorted by (value, position)."""
+    gd, gi = g_dist.numpy(), g_ind.numpy()
+    rows_d = np.stack([np.concatenate([gd[p * part_stride + r * k: p * part_stride + (r + 1) * k]
+                                       for p in range(nparts)]) for r in range(nq)])
+    rows_i = np.stack([np.concatenate([gi[p * part_stride + r * k: p * part_stride + (r + 1) * k]
+                                       for p in range(nparts)]) for r in range(nq)])
+    order = np.argsort(rows_d, axis=1, kind="stable")[:, :k]
+    return (torch.from_numpy(np.take_along_axis(rows_d, order, 1)),
+            torch.from_numpy(np.take_along_axis(rows_i, order, 1)))
+
+
+def _worker(rank, world, port, q, y, k, exclude_self, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        def local_search(lo, hi):
+            if hi <= lo:
+                return (torch.full((q.shape[0], k), float("inf"), dtype=torch.float64),
+                        torch.full((q.shape[0], k), -1, dtype=torch.int64))
+            kk = min(k, hi - lo)
+            d = O._pairwise(q, y[lo:hi], "euclidean")
+            if exclude_self:           # global column id == row id
+                rows = np.arange(q.shape[0])
+                inside = (rows >= lo) & (rows < hi)
+                d[rows[inside], rows[inside] - lo] = np.inf
+            order = np.argsort(d, axis=1, kind="stable")[:, :kk]
+            dd = np.full((q.shape[0], k), np.inf)
+            ii = np.full((q.shape[0], k), -1, dtype=np.int64)
+            dd[:, :kk] = np.take_along_axis(d, order, 1)
+            ii[:, :kk] = order + lo
+            ii[np.isinf(dd)] = -1
+            return torch.from_numpy(dd), torch.from_numpy(ii)
+
+        d, i = sharded_topk(local_search, _numpy_merge, y.shape[0], k)
+        out[rank] = (d.numpy(), i.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize(("nq", "ny", "k", "exclude_self"),
+                         [(37, 101, 5, False), (64, 64, 7, True), (5, 3, 2, False)])
+def test_sharded_topk_world2_gloo(nq, ny, k, exclude_self):
+    rng = np.random.default_rng(nq + ny)
+    y = rng.standard_normal((ny, 8))
+    q = y.copy() if exclude_self else rng.standard_normal((nq, 8))
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), q, y, k, exclude_self, out), nprocs=world, join=True)
+    want_d, want_i = O.knn_brute(q, y, k, exclude_self=exclude_self)
+    for rank in range(world):                      # replicated result on every rank
+        d, i = out[rank]
+        O.assert_neighbors_match(d, i, want_d, want_i, rtol=1e-12, atol=1e-12, what=f"rank{rank}")
+
+
+def test_shard_bounds_cover():
+    assert [shard_bounds(10, 3, r) for r in range(3)] == [(0, 4), (4, 7), (7, 10)]
+    assert shard_bounds(2, 4, 3) == (2, 2)
