@@ -24,6 +24,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU legs (cpu_baseline on rank 0,
+# --impl reference) must be allowed all host threads, so undo that before numpy/sklearn load.
+if os.environ.get("OMP_NUM_THREADS") == "1" and int(os.environ.get("RANK", "0")) == 0:
+    os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
+
 import numpy as np
 
 WORKLOADS = {

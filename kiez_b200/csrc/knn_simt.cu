@@ -22,8 +22,9 @@ knn_simt_kernel(const float *__restrict__ q_hi, const float *__restrict__ q_lo, 
     float *Bs = As + SIMT_K * SIMT_ROWS;                        // [SIMT_K][SIMT_COLS]
     RowLists L;
     L.cap = cap;
-    L.keys = Bs + SIMT_K * SIMT_COLS;                           // [SIMT_ROWS][cap]
-    L.cols = reinterpret_cast<int *>(L.keys + SIMT_ROWS * cap);
+    L.B = lists_buffer_slots(cap);
+    L.stride = lists_stride(cap, L.B);
+    L.ent = reinterpret_cast<ent_t *>(Bs + SIMT_K * SIMT_COLS);  // [SIMT_ROWS][stride]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t q0 = (int64_t)blockIdx.x * SIMT_ROWS;
@@ -35,6 +36,7 @@ knn_simt_kernel(const float *__restrict__ q_hi, const float *__restrict__ q_lo, 
 
     lists_reset(L, warp * 32, 32, lane);
     float tau = (row < nq) ? INFINITY : -INFINITY;
+    int cnt = 0;
 
     for (int64_t c0 = y_begin; c0 < y_end; c0 += SIMT_COLS) {
         float acc[SIMT_COLS];
@@ -103,9 +105,9 @@ knn_simt_kernel(const float *__restrict__ q_hi, const float *__restrict__ q_lo, 
             }
             v[j] = key;
         }
-        select_chunk<SIMT_COLS>(L, tid, v, (int)c0, tau, lane);
+        select_chunk<SIMT_COLS>(L, tid, v, (int)c0, tau, cnt, lane);
     }
-    __syncwarp();
+    lists_flush(L, tid, tau, cnt, lane);
     // write this split's lists: warp-cooperative, coalesced per row
     for (int r = 0; r < 32; ++r) {
         const int lr = warp * 32 + r;
@@ -113,8 +115,9 @@ knn_simt_kernel(const float *__restrict__ q_hi, const float *__restrict__ q_lo, 
         if (grow >= nq) break;
         for (int p = lane; p < cap; p += 32) {
             const int64_t o = grow * ((int64_t)splits * cap) + (int64_t)split * cap + p;
-            cand_idx[o] = L.cols[lr * cap + p];
-            if (cand_key) cand_key[o] = L.keys[lr * cap + p];
+            const ent_t e = L.ent[(size_t)lr * L.stride + p];
+            cand_idx[o] = entry_col(e);
+            if (cand_key) cand_key[o] = entry_key(e);
         }
     }
 }
@@ -124,7 +127,7 @@ int launch_knn_simt(const float *q_hi, const float *q_lo, int64_t nq, const floa
                     int splits, int exclude_self, int64_t self_offset, int32_t *cand_idx,
                     float *cand_key, cudaStream_t stream) {
     const size_t smem = (size_t)(SIMT_K * SIMT_ROWS + SIMT_K * SIMT_COLS) * sizeof(float) +
-                        (size_t)SIMT_ROWS * cap * (sizeof(float) + sizeof(int));
+                        lists_bytes(SIMT_ROWS, cap, lists_buffer_slots(cap));
     KB2_CUDA(cudaFuncSetAttribute(knn_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     dim3 grid((unsigned)ceil_div64(nq, SIMT_ROWS), (unsigned)splits);

@@ -155,7 +155,7 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
 struct TcParams {
     int64_t nq, ny;
     int kchunks;          // dpad / BK
-    int cap, splits, stages;
+    int cap, buf_slots, splits, stages;
     int exclude_self;
     int64_t self_offset;
     int64_t per_split;    // index rows per split (multiple of BN)
@@ -180,10 +180,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi,
     float *ykey_s = reinterpret_cast<float *>(stage_base + (size_t)P.stages * Cfg::STAGE_BYTES);
     RowLists L;
     L.cap = P.cap;
-    L.keys = ykey_s + 2 * BN;
-    L.cols = reinterpret_cast<int *>(L.keys + BM * P.cap);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(
-        (reinterpret_cast<uintptr_t>(L.cols + BM * P.cap) + 7) & ~(uintptr_t)7);
+    L.B = P.buf_slots;
+    L.stride = lists_stride(P.cap, P.buf_slots);
+    L.ent = reinterpret_cast<ent_t *>(ykey_s + 2 * BN);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(L.ent + (size_t)BM * L.stride);
     uint64_t *full_bar = bars;                         // [stages]
     uint64_t *empty_bar = bars + MAX_STAGES;           // [stages]
     uint64_t *tmem_full = bars + 2 * MAX_STAGES;       // [2]
@@ -319,6 +319,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi,
             const int64_t grow = qt * BM + lrow;
             lists_reset(L, warp * 32, 32, lane);
             float tau = (grow < P.nq) ? INFINITY : -INFINITY;
+            int cnt = 0;
             for (int64_t c0 = y_begin; c0 < y_end; c0 += BN) {
                 // stage this tile's selection terms (double-buffered by accumulator slot)
                 float *yk = ykey_s + acc * BN;
@@ -347,22 +348,23 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q_hi,
                                 if (j == (int)selfcol) v[j] = INFINITY;
                         }
                     }
-                    select_chunk<32>(L, lrow, v, (int)(c0 + ch * 32), tau, lane);
+                    select_chunk<32>(L, lrow, v, (int)(c0 + ch * 32), tau, cnt, lane);
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                 if (++acc == Cfg::NUM_ACC) { acc = 0; acc_phase ^= 1; }
             }
-            __syncwarp();
+            lists_flush(L, lrow, tau, cnt, lane);
             for (int r = 0; r < 32; ++r) {
                 const int lr = warp * 32 + r;
                 const int64_t gr = qt * BM + lr;
                 if (gr >= P.nq) break;
                 for (int p = lane; p < P.cap; p += 32) {
                     const int64_t o = gr * ((int64_t)P.splits * P.cap) + (int64_t)split * P.cap + p;
-                    P.cand_idx[o] = L.cols[lr * P.cap + p];
-                    if (P.cand_key) P.cand_key[o] = L.keys[lr * P.cap + p];
+                    const ent_t e = L.ent[(size_t)lr * L.stride + p];
+                    P.cand_idx[o] = entry_col(e);
+                    if (P.cand_key) P.cand_key[o] = entry_key(e);
                 }
             }
             __syncwarp();
@@ -416,9 +418,9 @@ static int make_map(CUtensorMap *map, const float *base, int64_t rows, int dpad,
 // Bytes the kernel carves out of dynamic shared memory, excluding the slack for
 // rounding the base up to 1024 B (the base is 1024-aligned in practice: there is no
 // static shared memory in this kernel; the kernel traps if the carve-up overflows).
-static size_t tc_smem_bytes(int bn, int stages, int cap) {
+static size_t tc_smem_bytes(int bn, int stages, int cap, int buf_slots) {
     const size_t stage = (size_t)(2 * BM + 2 * bn) * BK * 4;
-    return stages * stage + 2 * bn * sizeof(float) + (size_t)BM * cap * 8 + 8 /*align*/ +
+    return stages * stage + 2 * bn * sizeof(float) + lists_bytes(BM, cap, buf_slots) +
            (2 * MAX_STAGES + 4) * 8 + 16;
 }
 
@@ -434,7 +436,7 @@ static int launch_tc_bn(const TcParams &P0, const float *q_hi, const float *q_lo
     if (make_map(&mq_lo, q_lo, P.nq, dpad, BM)) return 1;
     if (make_map(&my_hi, y_hi, P.ny, dpad, BN)) return 1;
     if (make_map(&my_lo, y_lo, P.ny, dpad, BN)) return 1;
-    const size_t need = tc_smem_bytes(BN, stages, P.cap);
+    const size_t need = tc_smem_bytes(BN, stages, P.cap, P.buf_slots);
     const size_t smem = min((size_t)max_smem, need + 1024);
     KB2_CUDA(cudaFuncSetAttribute(knn_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
@@ -455,11 +457,21 @@ int launch_knn_tc(const float *q_hi, const float *q_lo, int64_t nq, const float 
     KB2_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     TcParams P;
     P.nq = nq; P.ny = ny; P.kchunks = dpad / BK; P.cap = cap; P.splits = splits; P.stages = 0;
-    P.exclude_self = exclude_self; P.self_offset = self_offset; P.per_split = 0;
+    P.exclude_self = exclude_self; P.self_offset = self_offset; P.per_split = 0; P.buf_slots = 16;
     P.q_tiles = ceil_div64(nq, BM); P.y_key = y_key; P.cand_idx = cand_idx; P.cand_key = cand_key;
+    // Append-buffer slots per row: more slots = fewer merges; shrink towards 16 when the
+    // lists would otherwise squeeze the operand pipeline below 2 stages.
+    auto stages_with = [&](int bn, int slots) {
+        const size_t fixed = tc_smem_bytes(bn, 0, cap, slots);
+        const size_t stage = (size_t)(2 * BM + 2 * bn) * BK * 4;
+        if (fixed >= (size_t)max_smem) return 0;
+        return (int)min((size_t)MAX_STAGES, ((size_t)max_smem - fixed) / stage);
+    };
+    P.buf_slots = lists_buffer_slots(cap);
+    while (P.buf_slots > 16 && stages_with(128, P.buf_slots) < 2) P.buf_slots -= 8;
     // widest tile whose pipeline still has >= 2 stages next to the candidate lists
     auto stages_for = [&](int bn) {
-        const size_t fixed = tc_smem_bytes(bn, 0, cap);
+        const size_t fixed = tc_smem_bytes(bn, 0, cap, P.buf_slots);
         const size_t stage = (size_t)(2 * BM + 2 * bn) * BK * 4;
         if (fixed >= (size_t)max_smem) return 0;
         return (int)min((size_t)MAX_STAGES, ((size_t)max_smem - fixed) / stage);

@@ -1,86 +1,177 @@
 // Running top-`cap` selection shared by the tcgen05 and the SIMT candidate-search
-// kernels.  One thread owns one query row (the TMEM lane it reads); each row has
-// a sorted list of its `cap` best (key, column) pairs in shared memory and the
-// owner keeps the list's current worst key `tau` in a register.  After the list
-// has filled, an element survives the `key < tau` test with probability
-// ~cap/position, so the common case is one compare per element; survivors are
-// inserted by the whole warp cooperating on the owner's list (cost independent
-// of which lane owns the row, no divergence).  Ties keep the earlier column,
-// like sklearn's heap (utils/_heap.pyx:46 rejects val >= heap_max).
+// kernels.  One thread owns one query row (the TMEM lane it reads).  Per row, shared
+// memory holds `cap` sorted best entries followed by an append buffer of `B` slots;
+// the owner keeps the list's worst key `tau` and the buffer fill `cnt` in registers.
+//
+//   per element : key < tau ?  -> the owner appends (key, col) to its buffer: one
+//                 predicated 64-bit store, no cross-lane traffic, no divergence
+//   per 8 elems : any row's buffer nearly full? -> the whole warp sorts that row's
+//                 list+buffer in registers (bitonic network over lanes x registers),
+//                 writes the best `cap` back and tightens tau
+//
+// Between merges tau is stale, so a few more elements pass than with an exact
+// threshold, but each costs a store instead of a serialized sorted insert: after the
+// list has filled an element passes with probability ~cap/position, and the number of
+// merges per row is ~log(m/cap)/log(1 + B/(2 cap)).
+// Entries are packed (order-preserving key bits << 32 | column): ties keep the lower
+// column, like sklearn's heap, which rejects val >= heap_max (utils/_heap.pyx:46).
 #pragma once
 #include "common.cuh"
 
 namespace kb2 {
 
+typedef unsigned long long ent_t;
+
+__device__ __forceinline__ ent_t pack_entry(float key, int col) {
+    unsigned u = __float_as_uint(key);
+    u ^= (u >> 31) ? 0xFFFFFFFFu : 0x80000000u;           // unsigned order == float order
+    return ((ent_t)u << 32) | (unsigned)col;
+}
+__device__ __forceinline__ float entry_key(ent_t e) {
+    unsigned u = (unsigned)(e >> 32);
+    u ^= (u >> 31) ? 0x80000000u : 0xFFFFFFFFu;
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ int entry_col(ent_t e) { return (int)(unsigned)(e & 0xFFFFFFFFu); }
+// +inf key, column -1
+constexpr ent_t EMPTY_ENTRY = ((ent_t)0xFF800000u << 32) | 0xFFFFFFFFull;
+
 struct RowLists {
-    float *keys;   // [rows][cap] ascending
-    int *cols;     // [rows][cap]
+    ent_t *ent;     // [rows][stride]: [0,cap) sorted list, [cap, cap+B) append buffer
     int cap;
+    int B;          // buffer slots, >= 16
+    int stride;     // cap + B entries per row
 };
 
+__host__ __device__ inline int lists_buffer_slots(int cap) {
+    int b = ((cap / 2 + 7) / 8) * 8;
+    return b < 16 ? 16 : (b > 64 ? 64 : b);
+}
+__host__ __device__ inline int lists_stride(int cap, int B) { return cap + B; }
+__host__ __device__ inline size_t lists_bytes(int rows, int cap, int B) {
+    return (size_t)rows * lists_stride(cap, B) * sizeof(ent_t);
+}
+
+// called by one warp for its own `rows` rows (only the sorted part needs a reset)
 __device__ __forceinline__ void lists_reset(const RowLists &L, int row_begin, int rows, int lane) {
-    // called by one warp for its own `rows` rows
-    for (int i = lane; i < rows * L.cap; i += 32) {
-        L.keys[row_begin * L.cap + i] = INFINITY;
-        L.cols[row_begin * L.cap + i] = -1;
-    }
+    for (int r = 0; r < rows; ++r)
+        for (int p = lane; p < L.cap; p += 32) L.ent[(size_t)(row_begin + r) * L.stride + p] = EMPTY_ENTRY;
     __syncwarp();
 }
 
-// Insert (nv, ncol) into the sorted list of `row`; all 32 lanes participate.
-// Returns the new worst key of the list (valid in every lane).
-static __device__ __noinline__ float list_insert(const RowLists &L, int row, float nv, int ncol,
-                                             int lane) {
-    float *k = L.keys + (size_t)row * L.cap;
-    int *c = L.cols + (size_t)row * L.cap;
-    constexpr int MAXT = 4;   // cap <= 128
-    float nk[MAXT];
-    int nc[MAXT];
+// Ascending bitonic sort of 32*R entries held as x[r] in lane `lane` <-> element r*32+lane.
+template <int R>
+__device__ __forceinline__ void warp_sort_entries(ent_t (&x)[R], int lane) {
+    constexpr int N = 32 * R;
 #pragma unroll
-    for (int t = 0; t < MAXT; ++t) {
-        const int p = lane + 32 * t;
-        if (p < L.cap) {
-            const float kp = k[p];
-            const int cp = c[p];
-            const float km = (p > 0) ? k[p - 1] : -INFINITY;
-            const int cm = (p > 0) ? c[p - 1] : -1;
-            if (kp <= nv) { nk[t] = kp; nc[t] = cp; }            // stays in place
-            else if (km <= nv) { nk[t] = nv; nc[t] = ncol; }     // insertion point
-            else { nk[t] = km; nc[t] = cm; }                     // shifted right by one
+    for (int size = 2; size <= N; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 32) {
+                const int rs = stride >> 5;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if ((r & rs) == 0) {
+                        const bool up = (((r * 32) & size) == 0);
+                        const ent_t a = x[r], b = x[r | rs];
+                        const bool sw = (a > b) == up;
+                        x[r] = sw ? b : a;
+                        x[r | rs] = sw ? a : b;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const ent_t other = __shfl_xor_sync(FULL_MASK, x[r], stride);
+                    const int e = r * 32 + lane;
+                    const bool up = ((e & size) == 0);
+                    const bool lower = ((lane & stride) == 0);
+                    const bool keep_min = (lower == up);
+                    const ent_t mn = x[r] < other ? x[r] : other;
+                    const ent_t mx = x[r] < other ? other : x[r];
+                    x[r] = keep_min ? mn : mx;
+                }
+            }
         }
     }
-    __syncwarp();
-#pragma unroll
-    for (int t = 0; t < MAXT; ++t) {
-        const int p = lane + 32 * t;
-        if (p < L.cap) { k[p] = nk[t]; c[p] = nc[t]; }
-    }
-    __syncwarp();
-    return k[L.cap - 1];
 }
 
-// Offer NV consecutive columns [col0, col0+NV) of this thread's row.
-// v[j] must already be +inf for masked columns.  `row` is the thread's list row,
-// `tau` its current threshold (-inf for rows that do not exist).
+// Merge the append buffer (first `cnt` slots valid) of one row into its sorted list.
+// All 32 lanes participate; returns the list's new worst key in every lane.
+template <int R>
+static __device__ __noinline__ float list_merge(ent_t *e, int cap, int stride, int cnt, int lane) {
+    ent_t x[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int idx = r * 32 + lane;
+        x[r] = (idx < cap + cnt && idx < stride) ? e[idx] : EMPTY_ENTRY;
+    }
+    warp_sort_entries<R>(x, lane);
+    ent_t worst = EMPTY_ENTRY;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int idx = r * 32 + lane;
+        if (idx < cap) e[idx] = x[r];
+        const ent_t w = __shfl_sync(FULL_MASK, x[r], (cap - 1) & 31);
+        if (r == ((cap - 1) >> 5)) worst = w;
+    }
+    __syncwarp();
+    return entry_key(worst);
+}
+
+__device__ __forceinline__ float list_merge_dispatch(const RowLists &L, int row, int cnt, int lane) {
+    ent_t *e = L.ent + (size_t)row * L.stride;
+    const int n = L.cap + L.B;
+    if (n <= 32) return list_merge<1>(e, L.cap, L.stride, cnt, lane);
+    if (n <= 64) return list_merge<2>(e, L.cap, L.stride, cnt, lane);
+    if (n <= 128) return list_merge<4>(e, L.cap, L.stride, cnt, lane);
+    return list_merge<8>(e, L.cap, L.stride, cnt, lane);
+}
+
+// Merge every row of this warp whose buffer fill satisfies `want` (warp-uniform loop).
+__device__ __forceinline__ void merge_rows(const RowLists &L, int row, float &tau, int &cnt,
+                                           bool want, int lane) {
+    unsigned need = __ballot_sync(FULL_MASK, want);
+    while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        const int r = __shfl_sync(FULL_MASK, row, src);
+        const int c = __shfl_sync(FULL_MASK, cnt, src);
+        __syncwarp();
+        const float t = list_merge_dispatch(L, r, c, lane);
+        if (lane == src) { tau = t; cnt = 0; }
+    }
+}
+
+// Offer NV (multiple of 8) consecutive columns [col0, col0+NV) of this thread's row.
+// v[j] must already be +inf for masked columns; `tau` = -inf for rows that do not exist.
 template <int NV>
 __device__ __forceinline__ void select_chunk(const RowLists &L, int row, const float (&v)[NV],
-                                             int col0, float &tau, int lane) {
+                                             int col0, float &tau, int &cnt, int lane) {
     float mn = v[0];
 #pragma unroll
     for (int j = 1; j < NV; ++j) mn = fminf(mn, v[j]);
     if (!__any_sync(FULL_MASK, mn < tau)) return;
+    ent_t *buf = L.ent + (size_t)row * L.stride + L.cap;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-        unsigned need = __ballot_sync(FULL_MASK, v[j] < tau);
-        while (need) {
-            const int src = __ffs(need) - 1;
-            need &= need - 1;
-            const float nv = __shfl_sync(FULL_MASK, v[j], src);
-            const int r = __shfl_sync(FULL_MASK, row, src);
-            const float t = list_insert(L, r, nv, col0 + j, lane);
-            if (lane == src) tau = t;
+    for (int g = 0; g < NV / 8; ++g) {
+#pragma unroll
+        for (int j = 8 * g; j < 8 * g + 8; ++j) {
+            if (v[j] < tau) {
+                buf[cnt] = pack_entry(v[j], col0 + j);
+                ++cnt;
+            }
         }
+        // a buffer with fewer than 8 free slots could overflow in the next group
+        if (__any_sync(FULL_MASK, cnt > L.B - 8)) merge_rows(L, row, tau, cnt, cnt > L.B - 8, lane);
     }
+}
+
+// After the last column: fold what is left in the buffers into the lists.
+__device__ __forceinline__ void lists_flush(const RowLists &L, int row, float &tau, int &cnt,
+                                            int lane) {
+    merge_rows(L, row, tau, cnt, cnt > 0, lane);
+    __syncwarp();
 }
 
 }  // namespace kb2
