@@ -39,9 +39,10 @@ extern "C" {
 #define KB2_RESCALE_MP_GAUSS  3 /* mutual_proximity.py:166-183, numpy branch       */
 
 /* which candidate-search kernel kb2_knn_candidates runs */
-#define KB2_KNN_AUTO  0 /* tcgen05 */
-#define KB2_KNN_TC    1 /* tcgen05/TMEM 3xTF32 tiles fed by TMA                  */
+#define KB2_KNN_AUTO  0 /* = KB2_KNN_TC */
+#define KB2_KNN_TC    1 /* tcgen05/TMEM 3xTF32 tiles fed by TMA, CTA pairs (cta_group::2) */
 #define KB2_KNN_SIMT  2 /* fp32 FFMA tiles; cross-check + debugging aid          */
+#define KB2_KNN_TC1   3 /* tcgen05, one CTA per tile (cross-check of the pair kernel)    */
 
 int kb2_version(void);
 const char *kb2_last_error(void);
@@ -80,16 +81,13 @@ int kb2_prepare_rows(const float *x, int64_t n, int d, int64_t ldx, const float 
  *   q_hi,q_lo [nq][dpad], y_hi,y_lo [ny][dpad], y_key [ny]
  *   splits    >=1: the index rows are cut into `splits` contiguous ranges, each
  *             searched by its own CTA set (fills the GPU when nq is small)
- *   exclude_self: drop column j where j + self_offset == row (sklearn X=None
- *             semantics, neighbors/_base.py:937-958)
  *   cand_idx  [nq][splits*cap] int32 out: LOCAL index row ids, -1 = empty slot
  *   cand_key  [nq][splits*cap] fp32 out or NULL (approximate keys; tests only)
  */
 int kb2_knn_candidates(int impl, const float *q_hi, const float *q_lo, int64_t nq,
                        const float *y_hi, const float *y_lo, const float *y_key,
-                       int64_t ny, int dpad, int cap, int splits, int exclude_self,
-                       int64_t self_offset, int32_t *cand_idx, float *cand_key,
-                       void *stream);
+                       int64_t ny, int dpad, int cap, int splits, int32_t *cand_idx,
+                       float *cand_key, void *stream);
 
 /*
  * Exact finish -- recomputes the distance of every candidate in float64 from
@@ -101,11 +99,16 @@ int kb2_knn_candidates(int impl, const float *q_hi, const float *q_lo, int64_t n
  *            README example keep their exact values for the finish)
  *   cand_idx [nq][ncand] local ids (-1 skipped); index_base is added on output
  *   q_sqnorm,y_sqnorm: fp64 ||.||^2 of the raw rows, cosine only (else NULL)
+ *   exclude_self: drop candidate j where j + self_offset == query row -- sklearn's
+ *            kneighbors(X=None) semantics (neighbors/_base.py:937-958).  The search keeps
+ *            the query's own row like any other candidate (it costs one of the list's
+ *            margin slots); it is removed here, by id.
  */
 int kb2_refine_topk(const void *q, int64_t nq, int64_t ldq, const void *y, int64_t ny,
                     int64_t ldy, int d, int elem_size, const double *q_sqnorm,
                     const double *y_sqnorm, const int32_t *cand_idx, int ncand, int metric,
-                    int64_t index_base, int k, double *out_dist, int64_t *out_ind, void *stream);
+                    int64_t index_base, int exclude_self, int64_t self_offset, int k,
+                    double *out_dist, int64_t *out_ind, void *stream);
 
 /*
  * Row-wise top-k of (dist, ind) pairs, ascending, ties by input position, NaN last.

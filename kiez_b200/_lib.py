@@ -11,11 +11,12 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libkiez_b200.so")
+# KB2_LIB selects another build of the same library (kernel A/B experiments only)
+LIB_PATH = os.environ.get("KB2_LIB") or os.path.join(_HERE, "lib", "libkiez_b200.so")
 
 METRIC_EUCLIDEAN, METRIC_SQEUCLIDEAN, METRIC_COSINE = 0, 1, 2
 RESCALE_CSLS, RESCALE_LS, RESCALE_NICDM, RESCALE_MP_GAUSS = 0, 1, 2, 3
-KNN_AUTO, KNN_TC, KNN_SIMT = 0, 1, 2
+KNN_AUTO, KNN_TC, KNN_SIMT, KNN_TC1 = 0, 1, 2, 3
 
 _p = C.c_void_p
 _i64 = C.c_int64
@@ -29,10 +30,9 @@ SIGNATURES = {
     "kb2_padded_dim": [_int],
     "kb2_suggest_splits": [_i64, _i64, _int, _int],
     "kb2_prepare_rows": [_p, _i64, _int, _i64, _p, _int, _p, _p, _int, _p, _p, _p],
-    "kb2_knn_candidates": [_int, _p, _p, _i64, _p, _p, _p, _i64, _int, _int, _int, _int, _i64,
-                           _p, _p, _p],
+    "kb2_knn_candidates": [_int, _p, _p, _i64, _p, _p, _p, _i64, _int, _int, _int, _p, _p, _p],
     "kb2_refine_topk": [_p, _i64, _i64, _p, _i64, _i64, _int, _int, _p, _p, _p, _int, _int, _i64,
-                        _int, _p, _p, _p],
+                        _int, _i64, _int, _p, _p, _p],
     "kb2_topk_rows": [_p, _p, _i64, _int, _int, _i64, _int, _p, _p, _p],
     "kb2_row_stats": [_p, _i64, _int, _p, _p, _p, _p],
     "kb2_rescale_topk": [_int, _p, _p, _i64, _int, _p, _p, _i64, _int, _p, _p, _p],

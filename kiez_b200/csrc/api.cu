@@ -1,5 +1,6 @@
 // C-ABI glue: error reporting, capability queries and the candidate-search dispatch.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -15,10 +16,11 @@ void set_error(const char *fmt, ...) {
 }
 
 int launch_knn_simt(const float *, const float *, int64_t, const float *, const float *,
-                    const float *, int64_t, int, int, int, int, int64_t, int32_t *, float *,
-                    cudaStream_t);
+                    const float *, int64_t, int, int, int, int32_t *, float *, cudaStream_t);
 int launch_knn_tc(const float *, const float *, int64_t, const float *, const float *, const float *,
-                  int64_t, int, int, int, int, int64_t, int32_t *, float *, cudaStream_t);
+                  int64_t, int, int, int, int32_t *, float *, cudaStream_t);
+int launch_knn_tc2(const float *, const float *, int64_t, const float *, const float *, const float *,
+                   int64_t, int, int, int, int32_t *, float *, cudaStream_t);
 
 }  // namespace kb2
 
@@ -42,9 +44,8 @@ extern "C" int kb2_suggest_splits(int64_t nq, int64_t ny, int cap, int sm_count)
 
 extern "C" int kb2_knn_candidates(int impl, const float *q_hi, const float *q_lo, int64_t nq,
                                   const float *y_hi, const float *y_lo, const float *y_key,
-                                  int64_t ny, int dpad, int cap, int splits, int exclude_self,
-                                  int64_t self_offset, int32_t *cand_idx, float *cand_key,
-                                  void *stream) {
+                                  int64_t ny, int dpad, int cap, int splits, int32_t *cand_idx,
+                                  float *cand_key, void *stream) {
     KB2_CHECK(nq >= 0 && ny > 0, "knn_candidates: bad shape nq=%lld ny=%lld", (long long)nq,
               (long long)ny);
     KB2_CHECK(nq < (1LL << 31) - 256 && ny < (1LL << 31) - 256,
@@ -54,12 +55,21 @@ extern "C" int kb2_knn_candidates(int impl, const float *q_hi, const float *q_lo
               kb2_max_candidates());
     KB2_CHECK(splits >= 1 && (int64_t)splits * cap <= 2048,
               "knn_candidates: splits*cap=%lld exceeds 2048", (long long)splits * cap);
-    KB2_CHECK(impl >= 0 && impl <= 2, "knn_candidates: unknown impl %d", impl);
+    KB2_CHECK(impl >= 0 && impl <= 3, "knn_candidates: unknown impl %d", impl);
     if (nq == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (impl == KB2_KNN_SIMT)
         return kb2::launch_knn_simt(q_hi, q_lo, nq, y_hi, y_lo, y_key, ny, dpad, cap, splits,
-                                    exclude_self, self_offset, cand_idx, cand_key, st);
-    return kb2::launch_knn_tc(q_hi, q_lo, nq, y_hi, y_lo, y_key, ny, dpad, cap, splits, exclude_self,
-                              self_offset, cand_idx, cand_key, st);
+                                    cand_idx, cand_key, st);
+    // tensor-core search: CTA-pair kernel unless the single-CTA one is asked for
+    // (impl KB2_KNN_TC1, or KB2_TC_MODE=1 in the environment for A/B runs)
+    const char *mode = getenv("KB2_TC_MODE");
+    const bool single = impl == KB2_KNN_TC1 || (mode && mode[0] == '1');
+    if (!single) {
+        const int rc = kb2::launch_knn_tc2(q_hi, q_lo, nq, y_hi, y_lo, y_key, ny, dpad, cap, splits,
+                                           cand_idx, cand_key, st);
+        if (rc >= 0) return rc;
+    }
+    return kb2::launch_knn_tc(q_hi, q_lo, nq, y_hi, y_lo, y_key, ny, dpad, cap, splits, cand_idx,
+                              cand_key, st);
 }

@@ -15,8 +15,7 @@ __global__ void __launch_bounds__(SIMT_ROWS)
 knn_simt_kernel(const float *__restrict__ q_hi, const float *__restrict__ q_lo, int64_t nq,
                 const float *__restrict__ y_hi, const float *__restrict__ y_lo,
                 const float *__restrict__ y_key, int64_t ny, int dpad, int cap, int splits,
-                int exclude_self, int64_t self_offset, int32_t *__restrict__ cand_idx,
-                float *__restrict__ cand_key) {
+                int32_t *__restrict__ cand_idx, float *__restrict__ cand_key) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *As = reinterpret_cast<float *>(smem_raw);            // [SIMT_K][SIMT_ROWS]
     float *Bs = As + SIMT_K * SIMT_ROWS;                        // [SIMT_K][SIMT_COLS]
@@ -99,10 +98,7 @@ knn_simt_kernel(const float *__restrict__ q_hi, const float *__restrict__ q_lo, 
         for (int j = 0; j < SIMT_COLS; ++j) {
             const int64_t col = c0 + j;
             float key = INFINITY;
-            if (col < y_end) {
-                key = fmaf(-2.f, acc[j], __ldg(y_key + col));
-                if (exclude_self && col + self_offset == row) key = INFINITY;
-            }
+            if (col < y_end) key = fmaf(-2.f, acc[j], __ldg(y_key + col));
             v[j] = key;
         }
         select_chunk<SIMT_COLS>(L, tid, v, (int)c0, tau, cnt, lane);
@@ -124,16 +120,14 @@ knn_simt_kernel(const float *__restrict__ q_hi, const float *__restrict__ q_lo, 
 
 int launch_knn_simt(const float *q_hi, const float *q_lo, int64_t nq, const float *y_hi,
                     const float *y_lo, const float *y_key, int64_t ny, int dpad, int cap,
-                    int splits, int exclude_self, int64_t self_offset, int32_t *cand_idx,
-                    float *cand_key, cudaStream_t stream) {
+                    int splits, int32_t *cand_idx, float *cand_key, cudaStream_t stream) {
     const size_t smem = (size_t)(SIMT_K * SIMT_ROWS + SIMT_K * SIMT_COLS) * sizeof(float) +
                         lists_bytes(SIMT_ROWS, cap, lists_buffer_slots(cap));
     KB2_CUDA(cudaFuncSetAttribute(knn_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     dim3 grid((unsigned)ceil_div64(nq, SIMT_ROWS), (unsigned)splits);
     knn_simt_kernel<<<grid, SIMT_ROWS, smem, stream>>>(q_hi, q_lo, nq, y_hi, y_lo, y_key, ny, dpad,
-                                                       cap, splits, exclude_self, self_offset,
-                                                       cand_idx, cand_key);
+                                                       cap, splits, cand_idx, cand_key);
     KB2_LAUNCH_CHECK();
     return 0;
 }

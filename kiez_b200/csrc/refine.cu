@@ -15,8 +15,8 @@ refine_topk_kernel(const T *__restrict__ q, int64_t nq, int64_t ldq,
                    const T *__restrict__ y, int64_t ny, int64_t ldy, int d,
                    const double *__restrict__ q_sqnorm, const double *__restrict__ y_sqnorm,
                    const int32_t *__restrict__ cand_idx, int ncand, int P, int metric,
-                   int64_t index_base, int k, double *__restrict__ out_dist,
-                   int64_t *__restrict__ out_ind) {
+                   int64_t index_base, int exclude_self, int64_t self_offset, int k,
+                   double *__restrict__ out_dist, int64_t *__restrict__ out_ind) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *key = reinterpret_cast<double *>(smem_raw) + (size_t)warp * P;
@@ -27,7 +27,8 @@ refine_topk_kernel(const T *__restrict__ q, int64_t nq, int64_t ldq,
     const T *qr = q + row * ldq;
     const int32_t *cr = cand_idx + row * (int64_t)ncand;
     for (int j = 0; j < P; ++j) {
-        const int32_t id = (j < ncand) ? cr[j] : -1;
+        int32_t id = (j < ncand) ? cr[j] : -1;
+        if (exclude_self && (int64_t)id + self_offset == row) id = -1;   // the query's own row
         double dist = INFINITY;
         if (id >= 0 && id < ny) {
             const T *yr = y + (int64_t)id * ldy;
@@ -122,14 +123,15 @@ template <typename T, bool VEC4>
 static int launch_refine(const void *q, int64_t nq, int64_t ldq, const void *y, int64_t ny,
                          int64_t ldy, int d, const double *q_sqnorm, const double *y_sqnorm,
                          const int32_t *cand_idx, int ncand, int P, int metric, int64_t index_base,
-                         int k, double *out_dist, int64_t *out_ind, cudaStream_t st) {
+                         int exclude_self, int64_t self_offset, int k, double *out_dist,
+                         int64_t *out_ind, cudaStream_t st) {
     using namespace kb2;
     const size_t smem = (size_t)REFINE_WARPS * P * 16;
     KB2_CUDA(cudaFuncSetAttribute(refine_topk_kernel<T, VEC4>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     refine_topk_kernel<T, VEC4><<<(unsigned)ceil_div64(nq, REFINE_WARPS), REFINE_WARPS * 32, smem, st>>>(
         static_cast<const T *>(q), nq, ldq, static_cast<const T *>(y), ny, ldy, d, q_sqnorm, y_sqnorm,
-        cand_idx, ncand, P, metric, index_base, k, out_dist, out_ind);
+        cand_idx, ncand, P, metric, index_base, exclude_self, self_offset, k, out_dist, out_ind);
     KB2_LAUNCH_CHECK();
     return 0;
 }
@@ -137,8 +139,9 @@ static int launch_refine(const void *q, int64_t nq, int64_t ldq, const void *y, 
 extern "C" int kb2_refine_topk(const void *q, int64_t nq, int64_t ldq, const void *y, int64_t ny,
                                int64_t ldy, int d, int elem_size, const double *q_sqnorm,
                                const double *y_sqnorm, const int32_t *cand_idx, int ncand,
-                               int metric, int64_t index_base, int k, double *out_dist,
-                               int64_t *out_ind, void *stream) {
+                               int metric, int64_t index_base, int exclude_self,
+                               int64_t self_offset, int k, double *out_dist, int64_t *out_ind,
+                               void *stream) {
     using namespace kb2;
     KB2_CHECK(nq >= 0 && ny > 0 && d > 0 && ldq >= d && ldy >= d, "refine_topk: bad shape");
     KB2_CHECK(elem_size == 4 || elem_size == 8, "refine_topk: elem_size must be 4 (fp32) or 8 (fp64)");
@@ -152,14 +155,15 @@ extern "C" int kb2_refine_topk(const void *q, int64_t nq, int64_t ldq, const voi
     cudaStream_t st = (cudaStream_t)stream;
     if (elem_size == 8)
         return launch_refine<double, false>(q, nq, ldq, y, ny, ldy, d, q_sqnorm, y_sqnorm, cand_idx,
-                                            ncand, P, metric, index_base, k, out_dist, out_ind, st);
+                                            ncand, P, metric, index_base, exclude_self, self_offset, k, out_dist, out_ind, st);
     const bool vec = (d % 4 == 0) && (ldq % 4 == 0) && (ldy % 4 == 0) &&
                      ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(y)) % 16 == 0);
     if (vec)
         return launch_refine<float, true>(q, nq, ldq, y, ny, ldy, d, q_sqnorm, y_sqnorm, cand_idx,
-                                          ncand, P, metric, index_base, k, out_dist, out_ind, st);
+                                          ncand, P, metric, index_base, exclude_self, self_offset, k, out_dist, out_ind, st);
     return launch_refine<float, false>(q, nq, ldq, y, ny, ldy, d, q_sqnorm, y_sqnorm, cand_idx, ncand,
-                                       P, metric, index_base, k, out_dist, out_ind, st);
+                                       P, metric, index_base, exclude_self, self_offset, k, out_dist,
+                                       out_ind, st);
 }
 
 extern "C" int kb2_topk_rows(const double *dist, const int64_t *ind, int64_t n, int c, int nparts,

@@ -5,7 +5,7 @@
 //
 //   per element : key < tau ?  -> the owner appends (key, col) to its buffer: one
 //                 predicated 64-bit store, no cross-lane traffic, no divergence
-//   per 8 elems : any row's buffer nearly full? -> the whole warp sorts that row's
+//   per 4 elems : any row's buffer nearly full? -> the whole warp sorts that row's
 //                 list+buffer in registers (bitonic network over lanes x registers),
 //                 writes the best `cap` back and tightens tau
 //
@@ -39,13 +39,15 @@ constexpr ent_t EMPTY_ENTRY = ((ent_t)0xFF800000u << 32) | 0xFFFFFFFFull;
 struct RowLists {
     ent_t *ent;     // [rows][stride]: [0,cap) sorted list, [cap, cap+B) append buffer
     int cap;
-    int B;          // buffer slots, >= 16
+    int B;          // buffer slots, >= LISTS_MIN_SLOTS
     int stride;     // cap + B entries per row
 };
 
+constexpr int LISTS_GROUP = 4;        // elements offered between two buffer-full checks
+constexpr int LISTS_MIN_SLOTS = 8;    // >= 2 * LISTS_GROUP
 __host__ __device__ inline int lists_buffer_slots(int cap) {
-    int b = ((cap / 2 + 7) / 8) * 8;
-    return b < 16 ? 16 : (b > 64 ? 64 : b);
+    int b = ((cap / 2 + LISTS_GROUP - 1) / LISTS_GROUP) * LISTS_GROUP;
+    return b < LISTS_MIN_SLOTS ? LISTS_MIN_SLOTS : (b > 64 ? 64 : b);
 }
 __host__ __device__ inline int lists_stride(int cap, int B) { return cap + B; }
 __host__ __device__ inline size_t lists_bytes(int rows, int cap, int B) {
@@ -143,27 +145,35 @@ __device__ __forceinline__ void merge_rows(const RowLists &L, int row, float &ta
     }
 }
 
-// Offer NV (multiple of 8) consecutive columns [col0, col0+NV) of this thread's row.
+// Offer NV (multiple of LISTS_GROUP) consecutive columns [col0, col0+NV) of this thread's row.
 // v[j] must already be +inf for masked columns; `tau` = -inf for rows that do not exist.
 template <int NV>
 __device__ __forceinline__ void select_chunk(const RowLists &L, int row, const float (&v)[NV],
                                              int col0, float &tau, int &cnt, int lane) {
-    float mn = v[0];
+    // chunk minimum as 4 independent chains (the lone epilogue warp of a scheduler is
+    // latency-bound: a single 31-deep dependent chain would cost ~5 clk per link)
+    float m4[4];
 #pragma unroll
-    for (int j = 1; j < NV; ++j) mn = fminf(mn, v[j]);
+    for (int q = 0; q < 4; ++q) {
+        m4[q] = v[q * (NV / 4)];
+#pragma unroll
+        for (int j = 1; j < NV / 4; ++j) m4[q] = fminf(m4[q], v[q * (NV / 4) + j]);
+    }
+    const float mn = fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
     if (!__any_sync(FULL_MASK, mn < tau)) return;
     ent_t *buf = L.ent + (size_t)row * L.stride + L.cap;
 #pragma unroll
-    for (int g = 0; g < NV / 8; ++g) {
+    for (int g = 0; g < NV / LISTS_GROUP; ++g) {
 #pragma unroll
-        for (int j = 8 * g; j < 8 * g + 8; ++j) {
+        for (int j = LISTS_GROUP * g; j < LISTS_GROUP * (g + 1); ++j) {
             if (v[j] < tau) {
                 buf[cnt] = pack_entry(v[j], col0 + j);
                 ++cnt;
             }
         }
-        // a buffer with fewer than 8 free slots could overflow in the next group
-        if (__any_sync(FULL_MASK, cnt > L.B - 8)) merge_rows(L, row, tau, cnt, cnt > L.B - 8, lane);
+        // a buffer with fewer than LISTS_GROUP free slots could overflow in the next group
+        const bool full = cnt > L.B - LISTS_GROUP;
+        if (__any_sync(FULL_MASK, full)) merge_rows(L, row, tau, cnt, full, lane);
     }
 }
 

@@ -192,8 +192,8 @@ class B200Mixin:
             raise ValueError(f"Unknown metric {metric}, please use one of {self.valid_metrics}")
         if metric == "minkowski" and p != 2:
             raise ValueError("B200 is an exact contraction backend: minkowski needs p=2")
-        if impl not in ("auto", "tc", "simt"):
-            raise ValueError(f"impl must be 'auto', 'tc' or 'simt', got {impl!r}")
+        if impl not in ("auto", "tc", "tc1", "simt"):
+            raise ValueError(f"impl must be 'auto', 'tc', 'tc1' or 'simt', got {impl!r}")
         super().__init__(n_candidates=n_candidates, metric=metric, n_jobs=n_jobs)
         self.p = p
         self.impl = impl
@@ -312,9 +312,11 @@ class B200Mixin:
                 splits = lib.lib.kb2_suggest_splits(q.n, y.n, cap, sm)
             ncand = splits * cap
             cand = torch.empty((q.n, ncand), dtype=torch.int32, device=dev)
-            impl = {"auto": lib.KNN_AUTO, "tc": lib.KNN_TC, "simt": lib.KNN_SIMT}[self.impl]
+            impl = {"auto": lib.KNN_AUTO, "tc": lib.KNN_TC, "simt": lib.KNN_SIMT,
+                    "tc1": lib.KNN_TC1}[self.impl]
             st = lib.stream_ptr()
-            # exclude column j where j + self_offset == row  (ids local to q / y)
+            # self = index row j with j + self_offset == query row (ids local to q / y); the
+            # search keeps it (one margin slot), the exact finish drops it by id
             self_offset = y.base - q.base
             prof = getattr(self, "_profile", None)   # bench.py: CUDA events around the search
             if prof is not None:
@@ -322,7 +324,7 @@ class B200Mixin:
                 ev0.record()
             lib.call("kb2_knn_candidates", impl, lib.ptr(q.hi), lib.ptr(q.lo), q.n,
                      lib.ptr(y.hi), lib.ptr(y.lo), lib.ptr(y.key), y.n, q.dpad, cap, splits,
-                     int(exclude_self), self_offset, lib.ptr(cand), None, st)
+                     lib.ptr(cand), None, st)
             if prof is not None:
                 ev1 = torch.cuda.Event(enable_timing=True)
                 ev1.record()
@@ -334,8 +336,8 @@ class B200Mixin:
             lib.call("kb2_refine_topk", lib.ptr(q_raw), q.n, q_raw.stride(0), lib.ptr(y_raw),
                      y.n, y_raw.stride(0), q.d, q_raw.element_size(), lib.ptr(q.sqnorm),
                      lib.ptr(y.sqnorm),
-                     lib.ptr(cand), ncand, self._metric_code, y.base, k,
-                     lib.ptr(out_d), lib.ptr(out_i), st)
+                     lib.ptr(cand), ncand, self._metric_code, y.base, int(exclude_self),
+                     self_offset, k, lib.ptr(out_d), lib.ptr(out_i), st)
         return out_d, out_i
 
 
@@ -343,7 +345,8 @@ class B200(B200Mixin, NNAlgorithm):
     """Exact kNN on one or more B200 GPUs; ``Kiez(algorithm="B200")``.
 
     Parameters mirror SklearnNN where they apply (n_candidates, metric, p, n_jobs).
-    ``impl``: "auto"/"tc" = tcgen05 tensor-core search, "simt" = FP32-pipe cross-check.
+    ``impl``: "auto"/"tc" = tcgen05 tensor-core search (CTA pairs), "tc1" = its single-CTA
+    form, "simt" = FP32-pipe cross-check.
     ``distributed``: shard the index side over the ranks of an initialised
     torch.distributed (NCCL) group; default: on when world_size > 1.
     """

@@ -63,16 +63,16 @@ def test_argument_validation_needs_no_device():
     from kiez_b200 import _lib
 
     with pytest.raises(RuntimeError, match="dpad"):
-        _lib.call("kb2_knn_candidates", 0, None, None, 10, None, None, None, 10, 33, 16, 1, 0, 0,
-                  None, None, None)
+        _lib.call("kb2_knn_candidates", 0, None, None, 10, None, None, None, 10, 33, 16, 1, None,
+                  None, None)
     with pytest.raises(RuntimeError, match="cap"):
-        _lib.call("kb2_knn_candidates", 0, None, None, 10, None, None, None, 10, 32, 500, 1, 0, 0,
-                  None, None, None)
+        _lib.call("kb2_knn_candidates", 0, None, None, 10, None, None, None, 10, 32, 500, 1, None,
+                  None, None)
     with pytest.raises(RuntimeError, match="k=0"):
         _lib.call("kb2_topk_rows", None, None, 4, 8, 1, 0, 0, None, None, None)
     with pytest.raises(RuntimeError, match="elem_size"):
-        _lib.call("kb2_refine_topk", None, 1, 4, None, 1, 4, 4, 2, None, None, None, 8, 0, 0, 1,
-                  None, None, None)
+        _lib.call("kb2_refine_topk", None, 1, 4, None, 1, 4, 4, 2, None, None, None, 8, 0, 0, 0, 0,
+                  1, None, None, None)
     assert isinstance(_lib.lib.kb2_last_error(), bytes)
 
 

@@ -44,7 +44,7 @@ def test_matches_reference_golden(name, metric, hub):
 
 
 @pytest.mark.parametrize("hub", list(HUB))
-@pytest.mark.parametrize("impl", ["tc", "simt"])
+@pytest.mark.parametrize("impl", ["tc", "tc1", "simt"])
 @pytest.mark.parametrize("single", [False, True])
 def test_matches_oracle_fresh_inputs(hub, impl, single):
     rng = np.random.default_rng(17)
@@ -131,3 +131,67 @@ def test_api_behaviour():
         Kiez(algorithm="B200").fit([[1.0, 2.0]], target)
     assert Kiez(algorithm=B200(metric="sqeuclidean"), hubness="DisSimLocal").hubness.squared
     assert "b200" in Kiez.show_algorithm_options()
+
+
+CONFIG_SHAPED = [
+    # BASELINE.json configs at oracle-sized row counts (same d, c, k, hubness as the named config)
+    ("c2", 3000, 3500, 256, 50, 10, "csls"),
+    ("c3-mp", 2500, 3000, 256, 100, 10, "mp_gaussian"),
+    ("c3-ls", 2500, 3000, 256, 100, 10, "ls"),
+    ("c3-nicdm", 2500, 3000, 256, 100, 10, "nicdm"),
+    ("c4", 5000, 6000, 256, 10, 10, "csls"),
+    ("c5-dsl", 3000, 9000, 128, 50, 10, "dsl"),
+    ("c5-nicdm", 3000, 9000, 128, 50, 10, "nicdm"),
+]
+
+
+@pytest.mark.parametrize(("name", "n", "m", "d", "c", "k", "hub"), CONFIG_SHAPED)
+def test_config_shaped_parity(name, n, m, d, c, k, hub):
+    rng = np.random.default_rng(abs(hash(name)) % 1000)
+    source = rng.standard_normal((n, d)).astype(np.float32)
+    target = rng.standard_normal((m, d)).astype(np.float32)
+    inst = _kiez(c, "euclidean", hub)
+    inst.fit(source, target)
+    dist, ind = inst.kneighbors(k)
+    want_d, want_i = O.kiez_kneighbors(source.astype(np.float64), target.astype(np.float64),
+                                       hubness=hub, n_candidates=c, k=k, knn=O.knn_sklearn)
+    O.assert_neighbors_match(dist, ind, want_d, want_i, RTOL, ATOL, what=name)
+
+
+def test_full_size_properties_c4_like():
+    """Size-independent properties at a size the oracle cannot run in full: sortedness,
+    id range, no duplicate ids, idempotence (same result twice), and oracle parity on a
+    random row sample (forward candidates are recomputed by brute force for those rows)."""
+    from kiez_b200 import hubness_score
+
+    n = m = 60000
+    d, c, k = 256, 10, 10
+    g = torch.Generator(device="cuda")
+    g.manual_seed(0)
+    source = torch.randn((n, d), generator=g, device="cuda")
+    target = torch.randn((m, d), generator=g, device="cuda")
+    inst = _kiez(c, "euclidean", "csls")
+    inst.fit(source, target)
+    dist, ind = inst.kneighbors(k)
+    dist2, ind2 = inst.kneighbors(k)
+    assert torch.equal(ind, ind2) and torch.equal(dist, dist2)
+    assert (torch.diff(dist, dim=1) >= 0).all()
+    assert int(ind.min()) >= 0 and int(ind.max()) < m
+    srt = torch.sort(ind, dim=1).values
+    assert (srt[:, 1:] != srt[:, :-1]).all()
+    # oracle on a row sample: CSLS needs the reverse statistics of every target the sample
+    # touches, so compute the reverse pass for exactly those targets
+    rows = np.random.default_rng(1).choice(n, 128, replace=False)
+    s64 = source.cpu().numpy().astype(np.float64)
+    t64 = target.cpu().numpy().astype(np.float64)
+    fwd_d, fwd_i = O.knn_brute(s64[rows], t64, c)
+    touched = np.unique(fwd_i)
+    rev_d, _ = O.knn_brute(t64[touched], s64, c)
+    r_train = np.zeros(m)
+    r_train[touched] = rev_d.mean(axis=1)
+    want = 2 * fwd_d - fwd_d.mean(axis=1, keepdims=True) - r_train[fwd_i]
+    want_d, want_i = O.sort_topk(want, fwd_i, k)
+    O.assert_neighbors_match(dist[rows].cpu().numpy(), ind[rows].cpu().numpy(), want_d, want_i,
+                             RTOL, ATOL, what="c4-like sample")
+    scores = hubness_score(ind, m, k=k, store_k_occurrence=True)
+    assert int(scores["k_occurrence"].sum()) == n * k          # checksum of the histogram

@@ -48,7 +48,7 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("impl", ["tc", "simt"])
+@pytest.mark.parametrize("impl", ["tc", "tc1", "simt"])
 @pytest.mark.parametrize(("nq", "ny", "d", "k"), SHAPES)
 @pytest.mark.parametrize("metric", ["euclidean", "cosine", "sqeuclidean"])
 def test_knn_matches_oracle(impl, nq, ny, d, k, metric):
@@ -67,7 +67,7 @@ def test_knn_matches_oracle(impl, nq, ny, d, k, metric):
                              what=f"rev {impl} {metric} {nq}x{ny}x{d}")
 
 
-@pytest.mark.parametrize("impl", ["tc", "simt"])
+@pytest.mark.parametrize("impl", ["tc", "tc1", "simt"])
 @pytest.mark.parametrize("dist_kind", ["shifted", "hubby"])
 def test_knn_hard_distributions(impl, dist_kind):
     q, y = _data(700, 1500, 96, seed=3, dist=dist_kind)
@@ -79,7 +79,7 @@ def test_knn_hard_distributions(impl, dist_kind):
                              what=f"{impl} {dist_kind}")
 
 
-@pytest.mark.parametrize("impl", ["tc", "simt"])
+@pytest.mark.parametrize("impl", ["tc", "tc1", "simt"])
 def test_self_query_excludes_self(impl):
     """sklearn kneighbors(X=None) semantics (neighbors/_base.py:937-958)."""
     q, _ = _data(600, 1, 40, seed=5)
@@ -101,7 +101,7 @@ def test_tc_and_simt_agree_with_many_splits():
     """Index splits (used to fill the GPU when there are few query tiles) + merge."""
     q, y = _data(200, 20000, 64, seed=9)
     outs = []
-    for impl in ("tc", "simt"):
+    for impl in ("tc", "tc1", "simt"):
         algo = _algo(n_candidates=10, impl=impl)
         qp, yp = algo._prepare(q, cache=False), algo._prepare(y, cache=False)
         for splits in (1, 3, 8):

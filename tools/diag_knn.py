@@ -18,9 +18,9 @@ def run(nq, ny, d, cap, splits, impl, seed=0, exclude_self=False):
     qp, yp = algo._prepare(q, cache=False), algo._prepare(y, cache=False)
     cand = torch.full((nq, splits * cap), -7, dtype=torch.int32, device="cuda")
     key = torch.full((nq, splits * cap), float("nan"), dtype=torch.float32, device="cuda")
-    code = {"tc": lib.KNN_TC, "simt": lib.KNN_SIMT}[impl]
+    code = {"tc": lib.KNN_TC, "tc1": lib.KNN_TC1, "simt": lib.KNN_SIMT}[impl]
     lib.call("kb2_knn_candidates", code, lib.ptr(qp.hi), lib.ptr(qp.lo), nq, lib.ptr(yp.hi),
-             lib.ptr(yp.lo), lib.ptr(yp.key), ny, qp.dpad, cap, splits, int(exclude_self), 0,
+             lib.ptr(yp.lo), lib.ptr(yp.key), ny, qp.dpad, cap, splits,
              lib.ptr(cand), lib.ptr(key), lib.stream_ptr())
     torch.cuda.synchronize()
     # float64 reference of the selection key
@@ -61,7 +61,8 @@ if __name__ == "__main__":
     for impl in impls:
         for (nq, ny, d, cap, splits) in [(128, 256, 32, 16, 1), (128, 512, 64, 16, 1),
                                          (100, 300, 40, 16, 1), (300, 1000, 256, 32, 1),
-                                         (256, 4096, 128, 64, 2), (130, 700, 96, 112, 1)]:
+                                         (256, 4096, 128, 64, 2), (130, 700, 96, 112, 1),
+                                         (700, 3000, 256, 16, 1), (1100, 5000, 128, 56, 3)]:
             ok &= check(nq, ny, d, cap, splits, impl)
     print("DIAG", "OK" if ok else "FAILED")
     sys.exit(0 if ok else 1)
