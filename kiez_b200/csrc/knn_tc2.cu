@@ -272,7 +272,7 @@ int launch_knn_tc2(const float *q_hi, const float *q_lo, int64_t nq, const float
             return 1;
         }
     } else {
-        bk = stages_for(32, P.buf_slots) >= 2 ? 32 : 16;
+        bk = stages_for(32, P.buf_slots) >= 2 ? 32 : 16;   // measured: 2 x 64 KB beats 4 x 32 KB
     }
     const int stages = stages_for(bk, P.buf_slots);
     if (stages < 2 || sm_count < 2) return -1;

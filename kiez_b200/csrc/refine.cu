@@ -117,6 +117,9 @@ topk_rows_kernel(const double *__restrict__ dist, const int64_t *__restrict__ in
     }
 }
 
+int launch_topk_rows_rg(const double *, const int64_t *, int64_t, int, int, int64_t, int, double *,
+                        int64_t *, cudaStream_t);   // rescale.cu, register-resident path
+
 }  // namespace kb2
 
 template <typename T, bool VEC4>
@@ -175,6 +178,9 @@ extern "C" int kb2_topk_rows(const double *dist, const int64_t *ind, int64_t n, 
     KB2_CHECK(total <= 2048, "topk_rows: %d candidates per row exceed 2048", total);
     KB2_CHECK(k > 0 && k <= total, "topk_rows: k=%d must be in (0, %d]", k, total);
     if (n == 0) return 0;
+    if (total <= 256)
+        return launch_topk_rows_rg(dist, ind, n, c, nparts, part_stride, k, out_dist, out_ind,
+                                   (cudaStream_t)stream);
     const int P = next_pow2(total);
     const size_t smem = (size_t)REFINE_WARPS * P * 24;
     KB2_CUDA(cudaFuncSetAttribute(topk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

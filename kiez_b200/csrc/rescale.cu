@@ -8,7 +8,7 @@
 //               nanmean / nanstd ddof=0 / scipy.stats.norm.sf)
 //   MP empiric  kiez/hubness_reduction/mutual_proximity.py:185-212
 //   DisSimLocal kiez/hubness_reduction/dis_sim.py:95-108,139-181
-#include "common.cuh"
+#include "rowgroup.cuh"
 
 namespace kb2 {
 
@@ -334,6 +334,206 @@ dsl_finish_kernel(const double *__restrict__ raw, const int64_t *__restrict__ in
     emit_row(b, c, P, k, row, lane, out_dist, out_ind);
 }
 
+// ---------------------------------------------------------------------------
+// register-resident fast path (c * nparts <= 256): see rowgroup.cuh
+// ---------------------------------------------------------------------------
+constexpr int RG_OP_TOPK = 4;        // plain row-wise top-k (final sort / multi-GPU merge)
+constexpr int RG_OP_DSL_FINISH = 5;  // DisSimLocal: shift by the global minimum, sqrt
+constexpr int RG_WARPS = 8;
+
+struct RgParams {
+    int op;                  // KB2_RESCALE_* or RG_OP_*
+    const double *dist;
+    const int64_t *ind;
+    int64_t n;
+    int c;                   // values per row and part
+    int nparts;              // row r = concat over parts p of dist[p*part_stride + r*c .. +c)
+    int64_t part_stride;
+    const double *stat_a, *stat_b;
+    int64_t n_stats;
+    const double *gmin;
+    int squared;
+    int k;                   // 0: write the unsorted transform
+    double *out_dist;
+    int64_t *out_ind;
+};
+
+template <int G, int E>
+__global__ void __launch_bounds__(RG_WARPS * 32)
+rows_rg_kernel(const RgParams p) {
+    const int lane = threadIdx.x & 31, gl = lane & (G - 1);
+    const int64_t row = ((int64_t)blockIdx.x * RG_WARPS + (threadIdx.x >> 5)) * (32 / G) + lane / G;
+    const bool row_ok = row < p.n;
+    const int total = p.c * p.nparts;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    double x[E];
+    int64_t off[E];
+    int64_t id[E];
+    double s = 0.0, sn = 0.0, cnt = 0.0;
+#pragma unroll
+    for (int t = 0; t < E; ++t) {
+        const int e = t * G + gl;
+        const bool ok = row_ok && e < total;
+        const int part = ok ? e / p.c : 0;
+        off[t] = (int64_t)part * p.part_stride + row * p.c + (e - part * p.c);
+        x[t] = ok ? p.dist[off[t]] : qnan;
+        id[t] = ok ? p.ind[off[t]] : -1;
+        if (ok) {
+            s += x[t];
+            if (!isnan(x[t])) { sn += x[t]; cnt += 1.0; }
+        }
+    }
+    double r[E];
+    if (p.op <= KB2_RESCALE_MP_GAUSS) {
+        const double mean = group_sum<G>(s) / (double)p.c;               // ndarray.mean
+        double mu = 0.0, sd = 0.0, last = 0.0;
+        if (p.op == KB2_RESCALE_LS) last = group_element<G, E>(x, p.c - 1, lane);
+        if (p.op == KB2_RESCALE_MP_GAUSS) {                              // nanmean / nanstd(ddof=0)
+            const double nn = group_sum<G>(cnt);
+            mu = group_sum<G>(sn) / nn;
+            double q = 0.0;
+#pragma unroll
+            for (int t = 0; t < E; ++t)
+                if (!isnan(x[t])) { const double d = x[t] - mu; q += d * d; }
+            sd = sqrt(group_sum<G>(q) / nn);
+        }
+#pragma unroll
+        for (int t = 0; t < E; ++t) {
+            const bool ok = id[t] >= 0 && id[t] < p.n_stats;
+            const double a = ok ? p.stat_a[id[t]] : qnan;
+            if (p.op == KB2_RESCALE_CSLS) {
+                r[t] = 2.0 * x[t] - mean - a;
+            } else if (p.op == KB2_RESCALE_LS) {
+                r[t] = 1.0 - exp(-1.0 * (x[t] * x[t]) / (last * a));
+            } else if (p.op == KB2_RESCALE_NICDM) {
+                r[t] = x[t] / sqrt(mean * a);
+            } else {
+                const double sb = ok ? p.stat_b[id[t]] : qnan;
+                r[t] = 1.0 - norm_sf(x[t], mu, sd) * norm_sf(x[t], a, sb);
+            }
+        }
+    } else if (p.op == RG_OP_DSL_FINISH) {
+        const double mn = *p.gmin;
+        const double shift = (mn < 0.0) ? -mn : 0.0;
+#pragma unroll
+        for (int t = 0; t < E; ++t) {
+            const double v = x[t] + shift;
+            r[t] = p.squared ? v : sqrt(v);
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < E; ++t) r[t] = x[t];
+    }
+    if (p.k == 0) {                                      // HubnessReduction.transform: unsorted
+#pragma unroll
+        for (int t = 0; t < E; ++t) {
+            const int e = t * G + gl;
+            if (row_ok && e < total) {
+                p.out_dist[row * total + e] = r[t];
+                p.out_ind[row * total + e] = id[t];
+            }
+        }
+        return;
+    }
+    int pos[E];
+#pragma unroll
+    for (int t = 0; t < E; ++t) {
+        const int e = t * G + gl;
+        const bool ok = row_ok && e < total;
+        pos[t] = ok ? e : RG_POS_PAD;
+        if (!ok) r[t] = qnan;
+    }
+    group_sort<G, E>(r, pos, gl);
+#pragma unroll
+    for (int t = 0; t < E; ++t) {
+        const int e = t * G + gl;                        // rank after the sort
+        if (row_ok && e < p.k) {
+            const int src = pos[t];
+            const int part = src / p.c;
+            p.out_dist[row * p.k + e] = r[t];
+            p.out_ind[row * p.k + e] =
+                p.ind[(int64_t)part * p.part_stride + row * p.c + (src - part * p.c)];
+        }
+    }
+}
+
+template <int G, int E>
+__global__ void __launch_bounds__(RG_WARPS * 32)
+row_stats_rg_kernel(const double *__restrict__ dist, int64_t n, int c, double *__restrict__ mean,
+                    double *__restrict__ sd, double *__restrict__ last) {
+    const int lane = threadIdx.x & 31, gl = lane & (G - 1);
+    const int64_t row = ((int64_t)blockIdx.x * RG_WARPS + (threadIdx.x >> 5)) * (32 / G) + lane / G;
+    const bool row_ok = row < n;
+    double x[E];
+    double s = 0.0, sn = 0.0, cnt = 0.0;
+#pragma unroll
+    for (int t = 0; t < E; ++t) {
+        const int e = t * G + gl;
+        const bool ok = row_ok && e < c;
+        x[t] = ok ? dist[row * c + e] : __longlong_as_double(0x7ff8000000000000LL);
+        if (ok) {
+            s += x[t];
+            if (!isnan(x[t])) { sn += x[t]; cnt += 1.0; }
+        }
+    }
+    s = group_sum<G>(s);
+    const double nn = group_sum<G>(cnt);
+    const double mu = group_sum<G>(sn) / nn;
+    double q = 0.0;
+#pragma unroll
+    for (int t = 0; t < E; ++t)
+        if (!isnan(x[t])) { const double d = x[t] - mu; q += d * d; }
+    q = group_sum<G>(q);
+    const double lst = group_element<G, E>(x, c - 1, lane);
+    if (row_ok && gl == 0) {
+        // `mean` serves CSLS/NICDM (plain mean) when sd == nullptr, MutualProximity otherwise
+        if (mean) mean[row] = sd ? mu : s / (double)c;
+        if (sd) sd[row] = sqrt(q / nn);
+        if (last) last[row] = lst;
+    }
+}
+
+// dispatch on the row width: G lanes x E registers >= width
+template <template <int, int> class Launcher, class... Args>
+static int rg_dispatch(int width, Args... args) {
+    if (width <= 8) return Launcher<8, 1>::run(args...);
+    if (width <= 16) return Launcher<16, 1>::run(args...);
+    if (width <= 32) return Launcher<32, 1>::run(args...);
+    if (width <= 64) return Launcher<32, 2>::run(args...);
+    if (width <= 128) return Launcher<32, 4>::run(args...);
+    return Launcher<32, 8>::run(args...);
+}
+template <int G, int E>
+struct RowsLauncher {
+    static int run(const RgParams &p, cudaStream_t st) {
+        const int64_t rows_per_block = (int64_t)RG_WARPS * (32 / G);
+        rows_rg_kernel<G, E><<<(unsigned)ceil_div64(p.n, rows_per_block), RG_WARPS * 32, 0, st>>>(p);
+        KB2_LAUNCH_CHECK();
+        return 0;
+    }
+};
+template <int G, int E>
+struct StatsLauncher {
+    static int run(const double *dist, int64_t n, int c, double *mean, double *sd, double *last,
+                   cudaStream_t st) {
+        const int64_t rows_per_block = (int64_t)RG_WARPS * (32 / G);
+        row_stats_rg_kernel<G, E><<<(unsigned)ceil_div64(n, rows_per_block), RG_WARPS * 32, 0, st>>>(
+            dist, n, c, mean, sd, last);
+        KB2_LAUNCH_CHECK();
+        return 0;
+    }
+};
+constexpr int RG_MAX_WIDTH = 256;
+
+int launch_topk_rows_rg(const double *dist, const int64_t *ind, int64_t n, int c, int nparts,
+                        int64_t part_stride, int k, double *out_dist, int64_t *out_ind,
+                        cudaStream_t st) {
+    RgParams p{};
+    p.op = RG_OP_TOPK; p.dist = dist; p.ind = ind; p.n = n; p.c = c; p.nparts = nparts;
+    p.part_stride = part_stride; p.k = k; p.out_dist = out_dist; p.out_ind = out_ind;
+    return rg_dispatch<RowsLauncher>(c * nparts, p, st);
+}
+
 }  // namespace kb2
 
 using namespace kb2;
@@ -344,6 +544,8 @@ extern "C" int kb2_row_stats(const double *dist, int64_t n, int c, double *mean,
                              double *last, void *stream) {
     KB2_CHECK(n >= 0 && c > 0, "row_stats: bad shape");
     if (n == 0) return 0;
+    if (c <= RG_MAX_WIDTH)
+        return rg_dispatch<StatsLauncher>(c, dist, n, c, mean, sd, last, (cudaStream_t)stream);
     row_stats_kernel<<<RS_GRID(n), 0, (cudaStream_t)stream>>>(dist, n, c, mean, sd, last);
     KB2_LAUNCH_CHECK();
     return 0;
@@ -363,6 +565,13 @@ extern "C" int kb2_rescale_topk(int mode, const double *dist, const int64_t *ind
     KB2_CHECK(stat_a != nullptr && (mode != KB2_RESCALE_MP_GAUSS || stat_b != nullptr),
               "rescale_topk: missing per-target statistics");
     if (n == 0) return 0;
+    if (c <= RG_MAX_WIDTH) {
+        RgParams p{};
+        p.op = mode; p.dist = dist; p.ind = ind; p.n = n; p.c = c; p.nparts = 1; p.part_stride = 0;
+        p.stat_a = stat_a; p.stat_b = stat_b; p.n_stats = n_stats; p.k = k;
+        p.out_dist = out_dist; p.out_ind = out_ind;
+        return rg_dispatch<RowsLauncher>(c, p, (cudaStream_t)stream);
+    }
     const int P = next_pow2(c);
     const size_t smem = (size_t)RS_WARPS * P * 24;
     KB2_CUDA(cudaFuncSetAttribute(rescale_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -445,6 +654,12 @@ extern "C" int kb2_dsl_finish_topk(const double *raw, const int64_t *ind, int64_
                                    int64_t *out_ind, void *stream) {
     if (check_row_args("dsl_finish_topk", n, c, k)) return 1;
     if (n == 0) return 0;
+    if (c <= RG_MAX_WIDTH) {
+        RgParams p{};
+        p.op = RG_OP_DSL_FINISH; p.dist = raw; p.ind = ind; p.n = n; p.c = c; p.nparts = 1;
+        p.gmin = global_min; p.squared = squared; p.k = k; p.out_dist = out_dist; p.out_ind = out_ind;
+        return rg_dispatch<RowsLauncher>(c, p, (cudaStream_t)stream);
+    }
     const int P = next_pow2(c);
     const size_t smem = (size_t)RS_WARPS * P * 24;
     KB2_CUDA(cudaFuncSetAttribute(dsl_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

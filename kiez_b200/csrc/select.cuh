@@ -164,6 +164,11 @@ __device__ __forceinline__ void select_chunk(const RowLists &L, int row, const f
     ent_t *buf = L.ent + (size_t)row * L.stride + L.cap;
 #pragma unroll
     for (int g = 0; g < NV / LISTS_GROUP; ++g) {
+        // most groups of a passing chunk still hold no survivor: skip them with one vote
+        bool any_pass = false;
+#pragma unroll
+        for (int j = LISTS_GROUP * g; j < LISTS_GROUP * (g + 1); ++j) any_pass |= (v[j] < tau);
+        if (!__any_sync(FULL_MASK, any_pass)) continue;
 #pragma unroll
         for (int j = LISTS_GROUP * g; j < LISTS_GROUP * (g + 1); ++j) {
             if (v[j] < tau) {
