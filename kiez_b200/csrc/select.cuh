@@ -5,9 +5,9 @@
 //
 //   per element : key < tau ?  -> the owner appends (key, col) to its buffer: one
 //                 predicated 64-bit store, no cross-lane traffic, no divergence
-//   per 4 elems : any row's buffer nearly full? -> the whole warp sorts that row's
-//                 list+buffer in registers (bitonic network over lanes x registers),
-//                 writes the best `cap` back and tightens tau
+//   per 4 elems : any row's buffer nearly full? -> the whole warp merges that row's
+//                 buffer into its list in registers (sort the buffer, then one bitonic
+//                 merge over lanes x registers), writes the best `cap` back, tightens tau
 //
 // Between merges tau is stale, so a few more elements pass than with an exact
 // threshold, but each costs a store instead of a serialized sorted insert: after the
@@ -45,6 +45,8 @@ struct RowLists {
 
 constexpr int LISTS_GROUP = 4;        // elements offered between two buffer-full checks
 constexpr int LISTS_MIN_SLOTS = 8;    // >= 2 * LISTS_GROUP
+// default: cap/2 rounded up to the group size, within [LISTS_MIN_SLOTS, 64]; list_merge
+// needs B <= 16 for cap <= 16 and B <= 32 for cap <= 32, which this satisfies
 __host__ __device__ inline int lists_buffer_slots(int cap) {
     int b = ((cap / 2 + LISTS_GROUP - 1) / LISTS_GROUP) * LISTS_GROUP;
     return b < LISTS_MIN_SLOTS ? LISTS_MIN_SLOTS : (b > 64 ? 64 : b);
@@ -98,17 +100,83 @@ __device__ __forceinline__ void warp_sort_entries(ent_t (&x)[R], int lane) {
     }
 }
 
-// Merge the append buffer (first `cnt` slots valid) of one row into its sorted list.
-// All 32 lanes participate; returns the list's new worst key in every lane.
-template <int R>
-static __device__ __noinline__ float list_merge(ent_t *e, int cap, int stride, int cnt, int lane) {
-    ent_t x[R];
+// One register per lane: lanes 0-15 sorted ascending, lanes 16-31 sorted descending
+// (a 16-element bitonic network per half-warp; xor strides <= 8 stay inside the half).
+__device__ __forceinline__ void warp_sort16_halves(ent_t &x, int lane) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int idx = r * 32 + lane;
-        x[r] = (idx < cap + cnt && idx < stride) ? e[idx] : EMPTY_ENTRY;
+    for (int size = 2; size <= 16; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const ent_t other = __shfl_xor_sync(FULL_MASK, x, stride);
+            const bool up = (((lane & 15) & size) == 0) != (lane >= 16);
+            const bool lower = ((lane & stride) == 0);
+            const bool keep_min = (lower == up);
+            const ent_t mn = x < other ? x : other;
+            const ent_t mx = x < other ? other : x;
+            x = keep_min ? mn : mx;
+        }
     }
-    warp_sort_entries<R>(x, lane);
+}
+
+// Ascending bitonic MERGE of 32*R entries whose first half is ascending and whose second
+// half is descending (log2(32R) compare-exchange steps instead of a full sort).
+template <int R>
+__device__ __forceinline__ void warp_merge_entries(ent_t (&x)[R], int lane) {
+#pragma unroll
+    for (int stride = 16 * R; stride > 0; stride >>= 1) {
+        if (stride >= 32) {
+            const int rs = stride >> 5;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if ((r & rs) == 0) {
+                    const ent_t a = x[r], b = x[r | rs];
+                    x[r] = a < b ? a : b;
+                    x[r | rs] = a < b ? b : a;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const ent_t other = __shfl_xor_sync(FULL_MASK, x[r], stride);
+                const bool lower = ((lane & stride) == 0);
+                const ent_t mn = x[r] < other ? x[r] : other;
+                const ent_t mx = x[r] < other ? other : x[r];
+                x[r] = lower ? mn : mx;
+            }
+        }
+    }
+}
+
+// Merge the append buffer (first `cnt` slots valid) of one row into its sorted list:
+// the list (ascending, <= 16R entries) fills the first half of a 32R-entry register
+// tile, the buffer is sorted DESCENDING into the tail of the second half (the rest is
+// +inf), and one bitonic merge yields the ascending union; the best `cap` go back.
+// All 32 lanes participate; returns the list's new worst key in every lane.
+// R = 1: cap <= 16, B <= 16 (halves are half-warps).  R >= 2: cap <= 16R, B <= 32*RB.
+template <int R, int RB>
+static __device__ __noinline__ float list_merge(ent_t *e, int cap, int cnt, int lane) {
+    ent_t x[R];
+    if constexpr (R == 1) {
+        const int j = lane - 16;
+        x[0] = (lane < cap) ? e[lane] : ((j >= 0 && j < cnt) ? e[cap + j] : EMPTY_ENTRY);
+        warp_sort16_halves(x[0], lane);
+    } else {
+        constexpr int TAIL = 32 * R - 32 * RB;           // first buffer position
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int idx = r * 32 + lane;
+            const int j = idx - TAIL;
+            x[r] = (idx < cap) ? e[idx] : ((j >= 0 && j < cnt) ? e[cap + j] : EMPTY_ENTRY);
+        }
+        // descending sort of the buffer registers = ascending sort of the complements
+        ent_t y[RB];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) y[r] = ~x[R - RB + r];
+        warp_sort_entries<RB>(y, lane);
+#pragma unroll
+        for (int r = 0; r < RB; ++r) x[R - RB + r] = ~y[r];
+    }
+    warp_merge_entries<R>(x, lane);
     ent_t worst = EMPTY_ENTRY;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -123,11 +191,11 @@ static __device__ __noinline__ float list_merge(ent_t *e, int cap, int stride, i
 
 __device__ __forceinline__ float list_merge_dispatch(const RowLists &L, int row, int cnt, int lane) {
     ent_t *e = L.ent + (size_t)row * L.stride;
-    const int n = L.cap + L.B;
-    if (n <= 32) return list_merge<1>(e, L.cap, L.stride, cnt, lane);
-    if (n <= 64) return list_merge<2>(e, L.cap, L.stride, cnt, lane);
-    if (n <= 128) return list_merge<4>(e, L.cap, L.stride, cnt, lane);
-    return list_merge<8>(e, L.cap, L.stride, cnt, lane);
+    if (L.cap <= 16) return list_merge<1, 1>(e, L.cap, cnt, lane);
+    if (L.cap <= 32) return list_merge<2, 1>(e, L.cap, cnt, lane);
+    if (L.cap <= 64)
+        return L.B <= 32 ? list_merge<4, 1>(e, L.cap, cnt, lane) : list_merge<4, 2>(e, L.cap, cnt, lane);
+    return L.B <= 32 ? list_merge<8, 1>(e, L.cap, cnt, lane) : list_merge<8, 2>(e, L.cap, cnt, lane);
 }
 
 // Merge every row of this warp whose buffer fill satisfies `want` (warp-uniform loop).
