@@ -57,7 +57,9 @@ def parse_args():
     ap.add_argument("--c", type=int)
     ap.add_argument("--k", type=int)
     ap.add_argument("--hubness", default=None)
-    ap.add_argument("--search-impl", default="auto", choices=["auto", "tc", "simt"])
+    ap.add_argument("--search-impl", default="auto", choices=["auto", "tc", "tc1", "simt"])
+    ap.add_argument("--fused", default="auto", choices=["auto", "on", "off"],
+                    help="dual-direction pass (one contraction for reverse + forward kNN)")
     ap.add_argument("--no-hub-scores", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -268,13 +270,17 @@ def run_b200(args, w):
 
     def make():
         algo = B200(n_candidates=w["c"], metric="euclidean", impl=args.search_impl,
-                    distributed=world > 1)
+                    distributed=world > 1,
+                    fused={"auto": "auto", "on": True, "off": False}[args.fused])
         return Kiez(n_candidates=w["c"], algorithm=algo, hubness=w["hubness"],
                     hubness_kwargs=dict(hub_kwargs))
+
+    out_algo = []
 
     def step(src, tgt, profile=None):
         inst = make()
         inst.algorithm._profile = profile
+        out_algo[:] = [inst.algorithm]
         inst.fit(src, tgt)
         dist_, ind_ = inst.kneighbors(w["k"])
         if not args.no_hub_scores:
@@ -308,22 +314,47 @@ def run_b200(args, w):
     ms_per_step = ms / args.steps
     value = w["n"] / (ms_per_step * 1e-3)
 
-    # roofline of the dominant kernel (candidate search) from CUDA events around its launches
-    k_ms = [a.elapsed_time(b) for (a, b, *_r) in profile]
-    k_flop = [2.0 * nq * ny * d for (_a, _b, nq, ny, d) in profile]
+    # roofline of the dominant kernel (candidate search) from CUDA events around its launches.
+    # Launches are grouped by shape; the group with the most algorithmic flops is the dominant
+    # kernel (the dual-direction pass, or the two one-direction passes), the others (threshold
+    # sample, overflow re-search) are listed beside it.
     peaks = measured_peaks()
     tf32_peak = peaks["bf16_sustained"] / 2.0
-    achieved = (sum(k_flop) / (sum(k_ms) * 1e-3) / 1e12) if k_ms else 0.0
+    groups = {}
+    for (a, b, nq, ny, d) in profile:
+        g = groups.setdefault((nq, ny, d), {"ms": 0.0, "n": 0})
+        g["ms"] += a.elapsed_time(b)
+        g["n"] += 1
+    detail = [{"nq": k[0], "ny": k[1], "d": k[2], "launches": v["n"],
+               "avg_launch_ms": v["ms"] / v["n"],
+               "algorithmic_tflops": 2.0 * k[0] * k[1] * k[2] / (v["ms"] / v["n"] * 1e-3) / 1e12}
+              for k, v in groups.items()]
+    detail.sort(key=lambda r: -r["nq"] * r["ny"])
+    search_ms = sum(v["ms"] for v in groups.values())
+    if detail:
+        top = [r for r in detail if r["nq"] * r["ny"] == detail[0]["nq"] * detail[0]["ny"]]
+        top_ms = sum(r["avg_launch_ms"] * r["launches"] for r in top)
+        top_n = sum(r["launches"] for r in top)
+        top_flop = 2.0 * top[0]["nq"] * top[0]["ny"] * top[0]["d"]
+        achieved = top_flop * top_n / (top_ms * 1e-3) / 1e12
+    else:
+        top_ms, top_n, top_flop, achieved = 0.0, 0, 0.0, 0.0
+    fused_stats = getattr(out_algo[0], "_fused_stats", None) if out_algo else None
     roofline = {
-        "bound": "tensor", "kernel": "knn_tc2_kernel (3xTF32 tcgen05 cta_group::2 + fused top-c)",
+        "bound": "tensor",
+        "kernel": ("knn_fused_kernel (3xTF32 tcgen05 cta_group::2, dual-direction, fused top-c)"
+                   if fused_stats else
+                   "knn_tc2_kernel (3xTF32 tcgen05 cta_group::2 + fused top-c)"),
         "achieved": achieved, "peak": tf32_peak / 3.0, "unit": "TFLOP/s",
         "frac": achieved / (tf32_peak / 3.0), "traffic": None,
         "issued_tf32_tflops": 3.0 * achieved, "tf32_peak": tf32_peak,
         "peak_source": f"{peaks['source']} bf16_tflops_sustained / 2 (TF32 rate) / 3 (3xTF32 "
                        "issues 3 MMAs per algorithmic MAC)",
-        "launches": len(k_ms), "avg_launch_ms": (sum(k_ms) / len(k_ms)) if k_ms else None,
-        "kernel_share_of_step": (sum(k_ms) / ms) if ms else None,
-        "algorithmic_flop_per_launch": (sum(k_flop) / len(k_flop)) if k_flop else None,
+        "launches": top_n, "avg_launch_ms": (top_ms / top_n) if top_n else None,
+        "kernel_share_of_step": (top_ms / ms) if ms else None,
+        "all_search_launches_share_of_step": (search_ms / ms) if ms else None,
+        "algorithmic_flop_per_launch": top_flop, "search_launches": detail,
+        "dual_direction": fused_stats,
     }
     if rank == 0:
         try:
@@ -370,7 +401,8 @@ def run_b200(args, w):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "tf32x3",
             "data": "synthetic",
             "config": {"workload": w["name"], "l2": "inputs (>=1 GB) exceed the 126 MB L2",
-                       "search_impl": args.search_impl, "hub_scores": not args.no_hub_scores,
+                       "search_impl": args.search_impl, "fused": args.fused,
+                       "hub_scores": not args.no_hub_scores,
                        "parallelism": f"index rows sharded over {world} GPU(s), NCCL all-gather + "
                                       "merge kernel" if world > 1 else "single GPU"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,

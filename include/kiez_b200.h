@@ -90,6 +90,25 @@ int kb2_knn_candidates(int impl, const float *q_hi, const float *q_lo, int64_t n
                        float *cand_key, void *stream);
 
 /*
+ * Dual-direction candidate search: one pass over the x (rows) x y (columns) tiles yields the
+ * row-wise candidate lists (as kb2_knn_candidates with queries = x, index = y) AND, per
+ * column, every row whose column key  x_key[row] - 2 <x,y>  is below tau_col[col], appended
+ * to col_buf[col][..col_cap) as packed (order-preserving key bits << 32 | row) with the count
+ * in col_cnt[col] (zeroed by the caller; counts above col_cap mean the column overflowed and
+ * must be searched separately).  tau_col must bound the column's final cap-th best key from
+ * above, e.g. the cap-th best key against a sample of the rows.  Serves kiez's reverse pass
+ * (hubness_reduction/base.py:37-42) and forward pass (:92-94) from ONE contraction.
+ */
+int kb2_knn_fused(const float *x_hi, const float *x_lo, const float *x_key, int64_t nx,
+                  const float *y_hi, const float *y_lo, const float *y_key, int64_t ny,
+                  int dpad, int cap, int splits, const float *tau_col, uint32_t *col_cnt,
+                  uint64_t *col_buf, int col_cap, int32_t *cand_idx, void *stream);
+/* Per column: the cap emitted rows with the smallest column keys -> cand_idx [ny][cap]
+ * (-1 padded), overflow[col] = 1 if more than col_cap rows were emitted. */
+int kb2_col_select(const uint64_t *col_buf, const uint32_t *col_cnt, int64_t ny, int col_cap,
+                   int cap, int32_t *cand_idx, int32_t *overflow, void *stream);
+
+/*
  * Exact finish -- recomputes the distance of every candidate in float64 from
  * the raw fp32 rows (the oracle upcasts fp32 to fp64 too,
  * sklearn _middle_term_computer.pyx.tp:309-318), sorts (distance, id)

@@ -31,6 +31,8 @@ SIGNATURES = {
     "kb2_suggest_splits": [_i64, _i64, _int, _int],
     "kb2_prepare_rows": [_p, _i64, _int, _i64, _p, _int, _p, _p, _int, _p, _p, _p],
     "kb2_knn_candidates": [_int, _p, _p, _i64, _p, _p, _p, _i64, _int, _int, _int, _p, _p, _p],
+    "kb2_knn_fused": [_p, _p, _p, _i64, _p, _p, _p, _i64, _int, _int, _int, _p, _p, _p, _int, _p, _p],
+    "kb2_col_select": [_p, _p, _i64, _int, _int, _p, _p, _p],
     "kb2_refine_topk": [_p, _i64, _i64, _p, _i64, _i64, _int, _int, _p, _p, _p, _int, _int, _i64,
                         _int, _i64, _int, _p, _p, _p],
     "kb2_topk_rows": [_p, _p, _i64, _int, _int, _i64, _int, _p, _p, _p],

@@ -222,12 +222,12 @@ __device__ __forceinline__ void load_ykey(const float *__restrict__ y_key, int64
 
 // One accumulator tile (this warp's 32 TMEM lanes x BN columns): key finish + selection.
 // `yk` = this warp's private shared copy of the tile's selection terms.
-template <int BN>
+template <int BN, bool DOUBLE_BUFFER = true>
 __device__ __forceinline__ void epilogue_tile(const RowLists &L, int lrow, const float *yk,
                                               uint32_t taddr, int64_t c0, float &tau, int &cnt,
                                               int lane) {
     constexpr int NCH = BN / 32;
-    uint32_t ra[32], rb[32];
+    uint32_t ra[32];
     auto process = [&](const uint32_t (&r)[32], int ch) {
         float v[32];
 #pragma unroll
@@ -235,6 +235,17 @@ __device__ __forceinline__ void epilogue_tile(const RowLists &L, int lrow, const
             v[j] = fmaf(-2.f, __uint_as_float(r[j]), yk[ch * 32 + j]);
         select_chunk<32>(L, lrow, v, (int)(c0 + ch * 32), tau, cnt, lane);
     };
+    if constexpr (!DOUBLE_BUFFER) {
+        // two epilogue warps per scheduler hide the TMEM latency; saves 32 registers
+#pragma unroll 1
+        for (int ch = 0; ch < NCH; ++ch) {
+            tmem_ld_32x32b_x32(taddr + ch * 32, ra);
+            tmem_ld_wait();
+            process(ra, ch);
+        }
+        return;
+    }
+    uint32_t rb[32];
     tmem_ld_32x32b_x32(taddr, ra);
 #pragma unroll 1
     for (int ch = 0; ch < NCH; ch += 2) {
@@ -302,8 +313,8 @@ static inline int make_map(CUtensorMap *map, const float *base, int64_t rows, in
 
 // Shared-memory bytes next to the operand stages: per-epilogue-warp y_key tile, the
 // candidate lists, the barriers.
-static inline size_t tc_fixed_smem(int bn, int cap, int buf_slots) {
-    return 4 * (size_t)bn * sizeof(float) + lists_bytes(BM, cap, buf_slots) +
+static inline size_t tc_fixed_smem(int bn, int cap, int buf_slots, int ykey_copies = 4) {
+    return (size_t)ykey_copies * bn * sizeof(float) + lists_bytes(BM, cap, buf_slots) +
            (2 * MAX_STAGES + 4) * 8 + 16;
 }
 

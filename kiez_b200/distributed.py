@@ -77,3 +77,39 @@ def sharded_knn(algo, q, index, k: int, exclude_self: bool, group=None):
         return algo.search(q, index.rows(lo, hi), k, exclude_self=exclude_self)
 
     return sharded_topk(local_search, device_merge, index.n, k, group=group)
+
+
+def sharded_knn_both(algo, rows, cols, k_fwd: int, k_rev: int, exclude_self_rows: bool, group=None):
+    """Distributed dual-direction pass.  Each rank owns a contiguous shard of the COLUMNS
+    (targets) and sees all rows (sources): its pass yields the row-wise lists over its shard
+    (merged across ranks like `sharded_knn`) and the COMPLETE column-wise result for its own
+    columns (every row was visited locally), which only needs an all-gather to be replicated.
+    Returns ((fwd_dist, fwd_ind), (rev_dist, rev_ind)), identical on every rank."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    lo, hi = shard_bounds(cols.n, world, rank)
+    dev = algo.device
+    if hi > lo:
+        (fd, fi), (rd, ri) = algo.search_both(rows, cols.rows(lo, hi), k_fwd, k_rev,
+                                              exclude_self_rows=exclude_self_rows)
+    else:
+        fd = torch.full((rows.n, k_fwd), float("inf"), dtype=torch.float64, device=dev)
+        fi = torch.full((rows.n, k_fwd), -1, dtype=torch.int64, device=dev)
+        rd = torch.empty((0, k_rev), dtype=torch.float64, device=dev)
+        ri = torch.empty((0, k_rev), dtype=torch.int64, device=dev)
+    fwd = sharded_topk(lambda _lo, _hi: (fd, fi), device_merge, cols.n, k_fwd, group=group)
+    # reverse: pad every shard to the largest shard, one packed all-gather, trim
+    per = -(-cols.n // world)
+    packed = torch.zeros(2 * per * k_rev, dtype=torch.int64, device=dev)
+    packed[: (hi - lo) * k_rev] = rd.contiguous().view(torch.int64).reshape(-1)
+    packed[per * k_rev: per * k_rev + (hi - lo) * k_rev] = ri.reshape(-1)
+    gathered = torch.empty(world * 2 * per * k_rev, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(gathered, packed, group=group)
+    g = gathered.view(world, 2, per, k_rev)
+    rev_d = torch.empty((cols.n, k_rev), dtype=torch.float64, device=dev)
+    rev_i = torch.empty((cols.n, k_rev), dtype=torch.int64, device=dev)
+    for r in range(world):
+        rlo, rhi = shard_bounds(cols.n, world, r)
+        rev_d[rlo:rhi] = g[r, 0, : rhi - rlo].view(torch.float64)
+        rev_i[rlo:rhi] = g[r, 1, : rhi - rlo]
+    return fwd, (rev_d, rev_i)

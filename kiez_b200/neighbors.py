@@ -159,6 +159,13 @@ class PreparedRows:
         self.base = base        # global id of row 0 (multi-GPU shards)
         self._owner = owner     # keeps the user's array alive while its id() is a cache key
 
+    def take(self, idx):
+        """The rows `idx` (a device int64 tensor) gathered into a new contiguous set."""
+        return PreparedRows(self.raw.index_select(0, idx), self.hi.index_select(0, idx),
+                            self.lo.index_select(0, idx), self.key.index_select(0, idx),
+                            None if self.sqnorm is None else self.sqnorm.index_select(0, idx),
+                            base=0, owner=self._owner)
+
     def rows(self, lo, hi):
         """A contiguous row shard (views, no copy)."""
         return PreparedRows(self.raw[lo:hi], self.hi[lo:hi], self.lo[lo:hi], self.key[lo:hi],
@@ -180,7 +187,7 @@ class B200Mixin:
 
     def __init__(self, n_candidates: int = 5, metric: str = "euclidean", p: int = 2,
                  device: Optional[Any] = None, impl: str = "auto", center: bool = True,
-                 distributed: Optional[bool] = None, n_jobs=None):
+                 distributed: Optional[bool] = None, fused: Any = "auto", n_jobs=None):
         if torch is None or not torch.cuda.is_available():
             raise ImportError(
                 "The B200 backend needs PyTorch with a CUDA device (sm_100a); there is no "
@@ -206,6 +213,10 @@ class B200Mixin:
             distributed = torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size() > 1
         self.distributed = bool(distributed)
+        if fused not in ("auto", True, False):
+            raise ValueError(f"fused must be 'auto', True or False, got {fused!r}")
+        self.fused = fused
+        self._fused_forward = None     # forward result cached by the dual-direction pass
         self._prepared = {}
         self._center_vec = None
         self._input_is_numpy = False
@@ -219,6 +230,7 @@ class B200Mixin:
     def fit(self, source, target=None, only_fit_target: bool = False):
         self._prepared = {}
         self._center_vec = None
+        self._fused_forward = None
         self._input_is_numpy = isinstance(source, np.ndarray)
         return super().fit(source, target, only_fit_target=only_fit_target)
 
@@ -233,7 +245,28 @@ class B200Mixin:
                 f"Expected n_neighbors <= n_samples_fit - 1, but n_neighbors = {k}, "
                 f"n_samples_fit = {index.n}"
             )
-        if self.distributed:
+        source_index = getattr(self, "source_index", None)
+        target_index = getattr(self, "target_index", None)
+        cached = self._fused_forward
+        if (cached is not None and index is target_index and q is source_index
+                and cached[0] == (k, bool(is_self_querying))):
+            dist, ind = cached[1]                        # forward pass already done by the fused pass
+        elif (index is source_index and q is target_index and not is_self_querying
+              and self._use_fused(source_index, target_index, k)):
+            # kiez's reverse pass (hubness_reduction/base.py:37-42): produce it together with the
+            # forward pass that HubnessReduction.kneighbors will ask for next (base.py:92-94)
+            single = bool(getattr(self, "source_equals_target", False))
+            k_fwd = min(self.n_candidates, target_index.n - (1 if single else 0))
+            if self.distributed:
+                from .distributed import sharded_knn_both
+
+                fwd, rev = sharded_knn_both(self, source_index, target_index, k_fwd, k, single)
+            else:
+                fwd, rev = self.search_both(source_index, target_index, k_fwd, k,
+                                            exclude_self_rows=single)
+            self._fused_forward = ((k_fwd, single), fwd)
+            dist, ind = rev
+        elif self.distributed:
             from .distributed import sharded_knn
 
             dist, ind = sharded_knn(self, q, index, k, is_self_querying)
@@ -289,6 +322,112 @@ class B200Mixin:
             self._prepared[id(data)] = prep
         return prep
 
+    # -- dual-direction pass ------------------------------------------------------
+    FUSED_EMIT_TARGET = 384      # expected rows emitted per column (sets the sample size)
+    FUSED_COL_CAP = 1024         # slots per column buffer
+
+    def _use_fused(self, rows: PreparedRows, cols: PreparedRows, k: int) -> bool:
+        if self.fused is False or self.impl in ("simt", "tc1"):
+            return False
+        cap = candidate_capacity(max(k, self.n_candidates))
+        if cap > 64 or rows.d != cols.d or rows.n < 2 * cap or cols.n < 1:
+            return False
+        if self.fused is True:
+            return True
+        # auto: only where the pass is tensor-bound (measured: with d = 128 or long candidate
+        # lists the doubled epilogue is the limiter and two passes are faster), and only for
+        # problems large enough to amortise the threshold sample
+        if cap > 32 or rows.dpad < 192 or rows.n * cols.n < (1 << 32):
+            return False
+        world = torch.distributed.get_world_size() if self.distributed else 1
+        free, _total = torch.cuda.mem_get_info(self.device)
+        return (cols.n // world + 1) * self.FUSED_COL_CAP * 8 < 0.4 * free
+
+    def search_both(self, rows: PreparedRows, cols: PreparedRows, k_rows: int, k_cols: int,
+                    exclude_self_rows: bool = False):
+        """One contraction, both directions: ((dist, ind) of every row's k_rows nearest columns,
+        (dist, ind) of every column's k_cols nearest rows)."""
+        lib = self._lib
+        dev = self.device
+        cap = candidate_capacity(max(k_rows, k_cols))
+        with torch.cuda.device(dev):
+            st = lib.stream_ptr()
+            sm = torch.cuda.get_device_properties(dev).multi_processor_count
+            # 1. column thresholds from a strided sample of the rows
+            n_s = min(rows.n, max(8 * cap, -(-rows.n * cap // self.FUSED_EMIT_TARGET)))
+            step = max(1, rows.n // n_s)
+            sample = rows.take(torch.arange(n_s, device=dev, dtype=torch.int64) * step)
+            s_splits = lib.lib.kb2_suggest_splits(cols.n, n_s, cap, sm)
+            s_idx = torch.empty((cols.n, s_splits * cap), dtype=torch.int32, device=dev)
+            s_key = torch.empty((cols.n, s_splits * cap), dtype=torch.float32, device=dev)
+            prof = getattr(self, "_profile", None)       # bench.py: CUDA events around the searches
+            if prof is not None:
+                ev0 = torch.cuda.Event(enable_timing=True)
+                ev0.record()
+            lib.call("kb2_knn_candidates", lib.KNN_AUTO, lib.ptr(cols.hi), lib.ptr(cols.lo), cols.n,
+                     lib.ptr(sample.hi), lib.ptr(sample.lo), lib.ptr(sample.key), n_s, rows.dpad,
+                     cap, s_splits, lib.ptr(s_idx), lib.ptr(s_key), st)
+            if prof is not None:
+                ev1 = torch.cuda.Event(enable_timing=True)
+                ev1.record()
+                prof.append((ev0, ev1, cols.n, n_s, rows.d))
+            # the cap-th best within ANY subset of the rows bounds the final cap-th best
+            tau = s_key.view(cols.n, s_splits, cap)[:, :, cap - 1].amin(dim=1).contiguous()
+            del s_idx, s_key
+            # 2. the dual-direction pass
+            splits = lib.lib.kb2_suggest_splits(rows.n, cols.n, cap, sm)
+            col_cap = self.FUSED_COL_CAP
+            col_cnt = torch.zeros(cols.n, dtype=torch.int32, device=dev)
+            col_buf = torch.empty((cols.n, col_cap), dtype=torch.int64, device=dev)
+            cand_rows = torch.empty((rows.n, splits * cap), dtype=torch.int32, device=dev)
+            if prof is not None:
+                ev0 = torch.cuda.Event(enable_timing=True)
+                ev0.record()
+            lib.call("kb2_knn_fused", lib.ptr(rows.hi), lib.ptr(rows.lo), lib.ptr(rows.key), rows.n,
+                     lib.ptr(cols.hi), lib.ptr(cols.lo), lib.ptr(cols.key), cols.n, rows.dpad, cap,
+                     splits, lib.ptr(tau), lib.ptr(col_cnt), lib.ptr(col_buf), col_cap,
+                     lib.ptr(cand_rows), st)
+            if prof is not None:
+                ev1 = torch.cuda.Event(enable_timing=True)
+                ev1.record()
+                prof.append((ev0, ev1, rows.n, cols.n, rows.d))
+            # 3. row side: exact finish of the row lists
+            fwd = self._refine(rows, cols, cand_rows, k_rows, exclude_self_rows)
+            # 4. column side: best cap emitted rows per column, exact finish
+            cand_cols = torch.empty((cols.n, cap), dtype=torch.int32, device=dev)
+            overflow = torch.empty(cols.n, dtype=torch.int32, device=dev)
+            lib.call("kb2_col_select", lib.ptr(col_buf), lib.ptr(col_cnt), cols.n, col_cap, cap,
+                     lib.ptr(cand_cols), lib.ptr(overflow), st)
+            del col_buf
+            rev_d, rev_i = self._refine(cols, rows, cand_cols, k_cols, False)
+            bad = torch.nonzero(overflow).flatten()
+            if prof is not None:
+                self._fused_stats = {"sample_rows": int(n_s), "col_cap": int(col_cap),
+                                     "emitted_per_column_mean": float(col_cnt.float().mean()),
+                                     "emitted_per_column_max": int(col_cnt.max()),
+                                     "overflow_columns": int(bad.numel())}
+            if bad.numel():      # columns whose buffer overflowed: plain search for those few
+                d_b, i_b = self.search(cols.take(bad), rows, k_cols)
+                rev_d[bad] = d_b
+                rev_i[bad] = i_b
+        return fwd, (rev_d, rev_i)
+
+    def _refine(self, q: PreparedRows, y: PreparedRows, cand, k: int, exclude_self: bool):
+        """Exact float64 finish of candidate lists `cand` (local ids into y)."""
+        lib = self._lib
+        dev = self.device
+        out_d = torch.empty((q.n, k), dtype=torch.float64, device=dev)
+        out_i = torch.empty((q.n, k), dtype=torch.int64, device=dev)
+        q_raw, y_raw = q.raw, y.raw
+        if q_raw.dtype != y_raw.dtype:
+            q_raw, y_raw = q_raw.to(torch.float64), y_raw.to(torch.float64)
+        # fewer than k valid candidates (a shard smaller than k) come back as +inf / -1
+        lib.call("kb2_refine_topk", lib.ptr(q_raw), q.n, q_raw.stride(0), lib.ptr(y_raw), y.n,
+                 y_raw.stride(0), q.d, q_raw.element_size(), lib.ptr(q.sqnorm), lib.ptr(y.sqnorm),
+                 lib.ptr(cand), cand.shape[1], self._metric_code, y.base, int(exclude_self),
+                 y.base - q.base, k, lib.ptr(out_d), lib.ptr(out_i), lib.stream_ptr())
+        return out_d, out_i
+
     def search(self, q: PreparedRows, y: PreparedRows, k: int, exclude_self: bool = False,
                splits: Optional[int] = None):
         """k nearest rows of `y` for every row of `q`: (dist float64, ind int64) on device,
@@ -329,15 +468,7 @@ class B200Mixin:
                 ev1 = torch.cuda.Event(enable_timing=True)
                 ev1.record()
                 prof.append((ev0, ev1, q.n, y.n, q.d))
-            q_raw, y_raw = q.raw, y.raw
-            if q_raw.dtype != y_raw.dtype:
-                q_raw, y_raw = q_raw.to(torch.float64), y_raw.to(torch.float64)
-            # fewer than k valid candidates (a shard smaller than k) come back as +inf / -1
-            lib.call("kb2_refine_topk", lib.ptr(q_raw), q.n, q_raw.stride(0), lib.ptr(y_raw),
-                     y.n, y_raw.stride(0), q.d, q_raw.element_size(), lib.ptr(q.sqnorm),
-                     lib.ptr(y.sqnorm),
-                     lib.ptr(cand), ncand, self._metric_code, y.base, int(exclude_self),
-                     self_offset, k, lib.ptr(out_d), lib.ptr(out_i), st)
+            out_d, out_i = self._refine(q, y, cand, k, exclude_self)
         return out_d, out_i
 
 

@@ -10,7 +10,7 @@ from oracle import kiez_oracle as O
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
-RTOL, ATOL = 1e-5, 1e-7
+RTOL, ATOL = 1e-5, 5e-6
 
 HUB = {
     "no": (None, {}),
@@ -23,18 +23,20 @@ HUB = {
 }
 
 
-def _kiez(c, metric, hub, impl="auto"):
+def _kiez(c, metric, hub, impl="auto", fused="auto"):
     from kiez_b200 import B200, Kiez
 
     name, kw = HUB[hub]
-    return Kiez(n_candidates=c, algorithm=B200(n_candidates=c, metric=metric, impl=impl),
+    return Kiez(n_candidates=c,
+                algorithm=B200(n_candidates=c, metric=metric, impl=impl, fused=fused),
                 hubness=name, hubness_kwargs=dict(kw))
 
 
 @pytest.mark.parametrize(("name", "metric", "hub"), _golden.cases())
-def test_matches_reference_golden(name, metric, hub):
+@pytest.mark.parametrize("fused", [False, True])
+def test_matches_reference_golden(name, metric, hub, fused):
     source, target, c, k, ref_dist, ref_ind = _golden.get(name, metric, hub)
-    inst = _kiez(c, metric, hub)
+    inst = _kiez(c, metric, hub, fused=fused)
     inst.fit(source, target)
     dist, ind = inst.kneighbors(k)
     assert isinstance(dist, np.ndarray) and dist.dtype == np.float64 and ind.dtype == np.int64
@@ -150,12 +152,13 @@ def test_config_shaped_parity(name, n, m, d, c, k, hub):
     rng = np.random.default_rng(abs(hash(name)) % 1000)
     source = rng.standard_normal((n, d)).astype(np.float32)
     target = rng.standard_normal((m, d)).astype(np.float32)
-    inst = _kiez(c, "euclidean", hub)
-    inst.fit(source, target)
-    dist, ind = inst.kneighbors(k)
     want_d, want_i = O.kiez_kneighbors(source.astype(np.float64), target.astype(np.float64),
                                        hubness=hub, n_candidates=c, k=k, knn=O.knn_sklearn)
-    O.assert_neighbors_match(dist, ind, want_d, want_i, RTOL, ATOL, what=name)
+    for fused in (False, True) if c <= 50 else (False,):
+        inst = _kiez(c, "euclidean", hub, fused=fused)
+        inst.fit(source, target)
+        dist, ind = inst.kneighbors(k)
+        O.assert_neighbors_match(dist, ind, want_d, want_i, RTOL, ATOL, what=f"{name} fused={fused}")
 
 
 def test_full_size_properties_c4_like():
