@@ -23,6 +23,8 @@
 namespace kb2 {
 
 constexpr int F_THREADS = 384;
+constexpr int EMIT_Q = 48;       // pending emits per column-epilogue warp; flushed above 16
+constexpr int EMIT_WORDS = 4 * EMIT_Q * 2 + 4 * EMIT_Q / 4;   // floats: keys + cols + lanes(bytes)
 constexpr int F_BN = 256;        // index (column) rows per tile of the CTA pair
 constexpr int F_HALF = 128;
 
@@ -33,6 +35,30 @@ struct FusedParams {
     ent_t *col_buf;              // [ny][col_cap] packed (column key, row)
     int col_cap;
 };
+
+// Drain up to 32 pending emits of a warp: lane i claims a slot of its entry's column buffer
+// (32 independent atomics in flight) and writes (column key, row); the rest moves down.
+__device__ __forceinline__ int emit_flush(const FusedParams &FP, float *qkey, int *qcol,
+                                          unsigned char *qlane, int qn, int64_t row_base, int lane) {
+    __syncwarp();
+    const int take = min(qn, 32);
+    float key = 0.f;
+    int col = 0, owner = 0;
+    if (lane < take) { key = qkey[lane]; col = qcol[lane]; owner = qlane[lane]; }
+    float key2 = 0.f;
+    int col2 = 0, owner2 = 0;
+    const bool more = lane + 32 < qn;
+    if (more) { key2 = qkey[lane + 32]; col2 = qcol[lane + 32]; owner2 = qlane[lane + 32]; }
+    if (lane < take) {
+        const unsigned int pos = atomicAdd(FP.col_cnt + col, 1u);
+        if (pos < (unsigned int)FP.col_cap)
+            FP.col_buf[(size_t)col * FP.col_cap + pos] = pack_entry(key, (int)(row_base + owner));
+    }
+    __syncwarp();
+    if (more) { qkey[lane] = key2; qcol[lane] = col2; qlane[lane] = (unsigned char)owner2; }
+    __syncwarp();
+    return qn - take;
+}
 
 template <int BK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1)
@@ -49,11 +75,15 @@ knn_fused_kernel(const __grid_constant__ CUtensorMap map_q_hi,
     unsigned char *stage_base = smem;
     // per epilogue warp a BN-float tile: warps 0-3 key_y, warps 4-7 tau_col
     float *tile_s = reinterpret_cast<float *>(stage_base + (size_t)P.stages * Cfg::STAGE_BYTES);
+    // per column-epilogue warp: a queue of pending emits (key, column, owner lane)
+    float *emit_key = tile_s + 8 * BN;                                   // [4][EMIT_Q]
+    int *emit_col = reinterpret_cast<int *>(emit_key + 4 * EMIT_Q);      // [4][EMIT_Q]
+    unsigned char *emit_lane = reinterpret_cast<unsigned char *>(emit_col + 4 * EMIT_Q);   // [4][EMIT_Q]
     RowLists L;
     L.cap = P.cap;
     L.B = P.buf_slots;
     L.stride = lists_stride(P.cap, P.buf_slots);
-    L.ent = reinterpret_cast<ent_t *>(tile_s + 8 * BN);
+    L.ent = reinterpret_cast<ent_t *>(tile_s + 8 * BN + EMIT_WORDS);
     uint64_t *bars = reinterpret_cast<uint64_t *>(L.ent + (size_t)BM * L.stride);
     uint64_t *full_bar = bars;
     uint64_t *empty_bar = bars + MAX_STAGES;
@@ -110,7 +140,16 @@ knn_fused_kernel(const __grid_constant__ CUtensorMap map_q_hi,
         // ------------------------------------------------------ TMA producer (both CTAs)
         int stage = 0;
         uint32_t phase = 0;
-        for (int64_t u = pair_id; u < num_units; u += num_pairs) {
+        int wave = 0;
+        for (int64_t u = pair_id; u < num_units; u += num_pairs, ++wave) {
+            if (P.wave_sync && wave > 0) {
+                // pairs taking part in this wave: those that still have a unit
+                const int64_t first = (int64_t)wave * num_pairs;
+                const unsigned int expected = (unsigned int)min(num_pairs, num_units - first);
+                if (rank == 0 && lane == 0) wave_barrier(wave, expected);
+                __syncwarp();
+                // the peer CTA's producer follows through the shared full/empty barriers
+            }
             const int64_t qt = 2 * (u % q_pairs) + rank;
             const int split = (int)(u / q_pairs);
             const int64_t y_begin = (int64_t)split * P.per_split;
@@ -220,6 +259,10 @@ knn_fused_kernel(const __grid_constant__ CUtensorMap map_q_hi,
         const int quad = warp - 4;                         // TMEM lane quadrant
         const int lrow = quad * 32 + lane;
         float *tk = tile_s + warp * BN;                    // this warp's tau_col tile
+        float *qkey = emit_key + quad * EMIT_Q;
+        int *qcol = emit_col + quad * EMIT_Q;
+        unsigned char *qlane = emit_lane + quad * EMIT_Q;
+        int qn = 0;                                        // pending emits (warp-uniform)
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int64_t u = pair_id; u < num_units; u += num_pairs) {
@@ -231,6 +274,7 @@ knn_fused_kernel(const __grid_constant__ CUtensorMap map_q_hi,
             // rows that do not exist never emit: -xk = -inf
             const float xk = (grow < P.nq) ? __ldg(FP.x_key + grow) : INFINITY;
             const float nxk = -xk;
+            const int64_t row_base = qt * BM + quad * 32;  // row of lane 0 of this warp
             float treg[BN / 32];
 #pragma unroll
             for (int t = 0; t < BN / 32; ++t) {
@@ -269,6 +313,9 @@ knn_fused_kernel(const __grid_constant__ CUtensorMap map_q_hi,
                     }
                     const float gmin = fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
                     if (!__any_sync(FULL_MASK, gmin < nxk)) continue;
+                    // Survivors go to the warp's queue (ballot-ranked, no atomics); the queue is
+                    // drained 17-48 entries at a time so that the global atomics that assign the
+                    // column-buffer slots are in flight together instead of one latency each.
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         bool any_pass = false;
@@ -277,13 +324,17 @@ knn_fused_kernel(const __grid_constant__ CUtensorMap map_q_hi,
                         if (!__any_sync(FULL_MASK, any_pass)) continue;
 #pragma unroll
                         for (int j = 4 * q; j < 4 * q + 4; ++j) {
-                            if (g[j] < nxk) {
-                                const int64_t col = c0 + ch * 32 + j;
-                                const unsigned int pos = atomicAdd(FP.col_cnt + col, 1u);
-                                if (pos < (unsigned int)FP.col_cap)
-                                    FP.col_buf[(size_t)col * FP.col_cap + pos] = pack_entry(
-                                        fmaf(-2.f, __uint_as_float(r[j]), xk), (int)grow);
+                            const bool pass = g[j] < nxk;
+                            const unsigned mask = __ballot_sync(FULL_MASK, pass);
+                            if (mask == 0) continue;
+                            if (pass) {
+                                const int slot = qn + __popc(mask & ((1u << lane) - 1));
+                                qkey[slot] = fmaf(-2.f, __uint_as_float(r[j]), xk);
+                                qcol[slot] = (int)(c0 + ch * 32 + j);
+                                qlane[slot] = (unsigned char)lane;
                             }
+                            qn += __popc(mask);
+                            if (qn > EMIT_Q - 32) qn = emit_flush(FP, qkey, qcol, qlane, qn, row_base, lane);
                         }
                     }
                 }
@@ -292,6 +343,7 @@ knn_fused_kernel(const __grid_constant__ CUtensorMap map_q_hi,
                 if (lane == 0) mbar_arrive_cluster(tmem_empty_leader + (uint32_t)acc * 8);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
+            while (qn > 0) qn = emit_flush(FP, qkey, qcol, qlane, qn, row_base, lane);   // rows change with the unit
         }
     }
 
@@ -355,12 +407,14 @@ static int launch_fused_cfg(const TcParams &P0, const FusedParams &FP, const flo
     if (make_map(&mq_lo, q_lo, P.nq, dpad, BM, BK)) return 1;
     if (make_map(&my_hi, y_hi, P.ny, dpad, F_HALF, BK)) return 1;
     if (make_map(&my_lo, y_lo, P.ny, dpad, F_HALF, BK)) return 1;
-    const size_t need = stages * fused_stage_bytes(BK) + tc_fixed_smem(F_BN, P.cap, P.buf_slots, 8);
+    const size_t need = stages * fused_stage_bytes(BK) + tc_fixed_smem(F_BN, P.cap, P.buf_slots, 8) +
+                        EMIT_WORDS * sizeof(float);
     const size_t smem = min((size_t)max_smem, need + 1024);
     KB2_CUDA(cudaFuncSetAttribute(knn_fused_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     const int64_t units = ((P.q_tiles + 1) / 2) * P.splits;
     const unsigned pairs = (unsigned)min((int64_t)(sm_count / 2), units);
+    if (prepare_wave_sync(P, units, pairs, false, stream)) return 1;
     knn_fused_kernel<BK><<<2 * pairs, F_THREADS, smem, stream>>>(mq_hi, mq_lo, my_hi, my_lo, P, FP);
     KB2_LAUNCH_CHECK();
     return 0;
@@ -388,13 +442,13 @@ extern "C" int kb2_knn_fused(const float *x_hi, const float *x_lo, const float *
     KB2_CHECK(sm_count >= 2, "knn_fused: needs CTA pairs");
     TcParams P;
     P.nq = nx; P.ny = ny; P.kchunks = 0; P.cap = cap; P.splits = splits; P.stages = 0;
-    P.per_split = 0; P.q_tiles = ceil_div64(nx, BM); P.y_key = y_key; P.cand_idx = cand_idx;
+    P.per_split = 0; P.wave_sync = 0; P.q_tiles = ceil_div64(nx, BM); P.y_key = y_key; P.cand_idx = cand_idx;
     P.cand_key = nullptr;
     FusedParams FP;
     FP.x_key = x_key; FP.tau_col = tau_col; FP.col_cnt = col_cnt;
     FP.col_buf = reinterpret_cast<ent_t *>(col_buf); FP.col_cap = col_cap;
     auto stages_for = [&](int bk, int slots) {
-        const size_t fixed = tc_fixed_smem(F_BN, cap, slots, 8);
+        const size_t fixed = tc_fixed_smem(F_BN, cap, slots, 8) + EMIT_WORDS * sizeof(float);
         if (fixed >= (size_t)max_smem) return 0;
         return (int)min((size_t)MAX_STAGES, ((size_t)max_smem - fixed) / fused_stage_bytes(bk));
     };

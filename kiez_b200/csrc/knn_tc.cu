@@ -252,7 +252,7 @@ int launch_knn_tc(const float *q_hi, const float *q_lo, int64_t nq, const float 
     KB2_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     TcParams P;
     P.nq = nq; P.ny = ny; P.kchunks = 0; P.cap = cap; P.splits = splits; P.stages = 0;
-    P.per_split = 0;
+    P.per_split = 0; P.wave_sync = 0;
     P.q_tiles = ceil_div64(nq, BM); P.y_key = y_key; P.cand_idx = cand_idx; P.cand_key = cand_key;
     auto stages_for = [&](int bn, int bk, int slots) {
         const size_t fixed = tc_fixed_smem(bn, cap, slots);

@@ -100,7 +100,16 @@ knn_tc2_kernel(const __grid_constant__ CUtensorMap map_q_hi,
         // ------------------------------------------------------ TMA producer (both CTAs)
         int stage = 0;
         uint32_t phase = 0;
-        for (int64_t u = pair_id; u < num_units; u += num_pairs) {
+        int wave = 0;
+        for (int64_t u = pair_id; u < num_units; u += num_pairs, ++wave) {
+            if (P.wave_sync && wave > 0) {
+                // pairs taking part in this wave: those that still have a unit
+                const int64_t first = (int64_t)wave * num_pairs;
+                const unsigned int expected = (unsigned int)min(num_pairs, num_units - first);
+                if (rank == 0 && lane == 0) wave_barrier(wave, expected);
+                __syncwarp();
+                // the peer CTA's producer follows through the shared full/empty barriers
+            }
             const int64_t qt = 2 * (u % q_pairs) + rank;
             const int split = (int)(u / q_pairs);
             const int64_t y_begin = (int64_t)split * P.per_split;
@@ -240,6 +249,7 @@ static int launch_tc2_cfg(const TcParams &P0, const float *q_hi, const float *q_
                                   (int)smem));
     const int64_t units = ((P.q_tiles + 1) / 2) * P.splits;
     const unsigned pairs = (unsigned)min((int64_t)(sm_count / 2), units);
+    if (prepare_wave_sync(P, units, pairs, true, stream)) return 1;
     knn_tc2_kernel<BK><<<2 * pairs, TC_THREADS, smem, stream>>>(mq_hi, mq_lo, my_hi, my_lo, P);
     KB2_LAUNCH_CHECK();
     return 0;
@@ -255,7 +265,7 @@ int launch_knn_tc2(const float *q_hi, const float *q_lo, int64_t nq, const float
     KB2_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     TcParams P;
     P.nq = nq; P.ny = ny; P.kchunks = 0; P.cap = cap; P.splits = splits; P.stages = 0;
-    P.per_split = 0;
+    P.per_split = 0; P.wave_sync = 0;
     P.q_tiles = ceil_div64(nq, BM); P.y_key = y_key; P.cand_idx = cand_idx; P.cand_key = cand_key;
     auto stages_for = [&](int bk, int slots) {
         const size_t fixed = tc_fixed_smem(PAIR_BN, cap, slots);

@@ -197,7 +197,31 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
            ((uint32_t)(M >> 4) << 24);
 }
 
+// Wave barrier of the persistent CTA-pair kernels: before a pair's producer starts the
+// loads of its w-th work unit it waits until every pair that has a w-th unit has finished
+// loading its (w-1)-th.  All pairs then sweep the index tiles of a wave in step, which is
+// what lets them share each tile through L2 instead of each streaming it from HBM (pairs
+// that drift apart by more than the L2 capacity, ~4 % of a 1M-row sweep, stop sharing).
+// Safe to spin: the grid never exceeds one CTA per SM, so all pairs are co-resident.
+constexpr int MAX_WAVES = 8192;
+__device__ unsigned int g_wave_arrivals[MAX_WAVES];
+
+__device__ __forceinline__ void wave_barrier(int wave, unsigned int expected) {
+    // called by ONE thread per CTA pair
+    __threadfence();
+    atomicAdd(&g_wave_arrivals[wave], 1u);
+    const long long t0 = clock64();
+    while (atomicAdd(&g_wave_arrivals[wave], 0u) < expected) {
+        __nanosleep(200);
+        if (clock64() - t0 > 8000000000LL) {
+            printf("kiez_b200: wave barrier timed out (block %d wave %d)\n", blockIdx.x, wave);
+            __trap();
+        }
+    }
+}
+
 struct TcParams {
+    int wave_sync;        // 1: producers meet at every work-unit boundary (wave_barrier)
     int64_t nq, ny;
     int kchunks;          // dpad / BK
     int cap, buf_slots, splits, stages;
@@ -308,6 +332,26 @@ static inline int make_map(CUtensorMap *map, const float *base, int64_t rows, in
                      bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     KB2_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+
+// Arms the wave barrier for one launch (stream-ordered reset of the arrival counters).
+// The counters are one per-device array: launches of the pair kernels on different streams
+// of the same device must not overlap (the host classes use one stream).
+// Measured at C4 (profiles/r01_ab_experiments.md block G): the one-direction pair kernel gains
+// (DRAM reads halve, clocks under the power cap rise), the dual-direction kernel loses (its
+// column epilogue makes unit times uneven) -> `default_on` differs; KB2_WAVE_SYNC=0/1 overrides.
+static inline int prepare_wave_sync(TcParams &P, int64_t units, unsigned pairs, bool default_on,
+                                    cudaStream_t stream) {
+    const int64_t waves = (units + pairs - 1) / pairs;
+    const char *env = getenv("KB2_WAVE_SYNC");
+    const bool on = env ? env[0] != '0' : default_on;
+    P.wave_sync = (waves > 1 && waves <= MAX_WAVES && on) ? 1 : 0;
+    if (P.wave_sync) {
+        void *addr = nullptr;
+        KB2_CUDA(cudaGetSymbolAddress(&addr, g_wave_arrivals));
+        KB2_CUDA(cudaMemsetAsync(addr, 0, (size_t)waves * sizeof(unsigned int), stream));
+    }
     return 0;
 }
 
