@@ -60,6 +60,9 @@ def parse_args():
     ap.add_argument("--search-impl", default="auto", choices=["auto", "tc", "tc1", "simt"])
     ap.add_argument("--fused", default="auto", choices=["auto", "on", "off"],
                     help="dual-direction pass (one contraction for reverse + forward kNN)")
+    ap.add_argument("--precision", default="auto", choices=["auto", "tf32x3", "screen"],
+                    help="candidate search: 3xTF32 keys, or 1xTF32 screen + float64 proof + 3xTF32 "
+                         "re-search of unproven rows (same results)")
     ap.add_argument("--no-hub-scores", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -270,7 +273,7 @@ def run_b200(args, w):
 
     def make():
         algo = B200(n_candidates=w["c"], metric="euclidean", impl=args.search_impl,
-                    distributed=world > 1,
+                    distributed=world > 1, precision=args.precision,
                     fused={"auto": "auto", "on": True, "off": False}[args.fused])
         return Kiez(n_candidates=w["c"], algorithm=algo, hubness=w["hubness"],
                     hubness_kwargs=dict(hub_kwargs))
@@ -321,40 +324,50 @@ def run_b200(args, w):
     peaks = measured_peaks()
     tf32_peak = peaks["bf16_sustained"] / 2.0
     groups = {}
-    for (a, b, nq, ny, d) in profile:
-        g = groups.setdefault((nq, ny, d), {"ms": 0.0, "n": 0})
+    for (a, b, nq, ny, d, kind) in profile:
+        g = groups.setdefault((nq, ny, d, kind), {"ms": 0.0, "n": 0})
         g["ms"] += a.elapsed_time(b)
         g["n"] += 1
-    detail = [{"nq": k[0], "ny": k[1], "d": k[2], "launches": v["n"],
+    detail = [{"nq": k[0], "ny": k[1], "d": k[2], "kind": k[3], "launches": v["n"],
                "avg_launch_ms": v["ms"] / v["n"],
                "algorithmic_tflops": 2.0 * k[0] * k[1] * k[2] / (v["ms"] / v["n"] * 1e-3) / 1e12}
               for k, v in groups.items()]
     detail.sort(key=lambda r: -r["nq"] * r["ny"])
     search_ms = sum(v["ms"] for v in groups.values())
     if detail:
-        top = [r for r in detail if r["nq"] * r["ny"] == detail[0]["nq"] * detail[0]["ny"]]
+        top = [r for r in detail if r["nq"] * r["ny"] == detail[0]["nq"] * detail[0]["ny"]
+               and r["kind"] == detail[0]["kind"]]
         top_ms = sum(r["avg_launch_ms"] * r["launches"] for r in top)
         top_n = sum(r["launches"] for r in top)
         top_flop = 2.0 * top[0]["nq"] * top[0]["ny"] * top[0]["d"]
         achieved = top_flop * top_n / (top_ms * 1e-3) / 1e12
+        kind = top[0]["kind"]
     else:
-        top_ms, top_n, top_flop, achieved = 0.0, 0, 0.0, 0.0
+        top_ms, top_n, top_flop, achieved, kind = 0.0, 0, 0.0, 0.0, "tf32x3"
     fused_stats = getattr(out_algo[0], "_fused_stats", None) if out_algo else None
+    search_stats = dict(getattr(out_algo[0], "search_stats", {})) if out_algo else {}
+    mmas = 1.0 if kind.startswith("screen") else 3.0      # MMAs issued per algorithmic MAC
+    kernel_names = {
+        "screen-dual": "knn_screen_kernel<dual> (1xTF32 tcgen05 cta_group::2, resident query tile, "
+                       "dual-direction, fused top-c; float64 proof + 3xTF32 re-search of unproven rows)",
+        "screen": "knn_screen_kernel (1xTF32 tcgen05 cta_group::2, resident query tile, fused top-c; "
+                  "float64 proof + 3xTF32 re-search of unproven rows)",
+        "tf32x3-dual": "knn_fused_kernel (3xTF32 tcgen05 cta_group::2, dual-direction, fused top-c)",
+        "tf32x3": "knn_tc2_kernel (3xTF32 tcgen05 cta_group::2 + fused top-c)",
+    }
     roofline = {
         "bound": "tensor",
-        "kernel": ("knn_fused_kernel (3xTF32 tcgen05 cta_group::2, dual-direction, fused top-c)"
-                   if fused_stats else
-                   "knn_tc2_kernel (3xTF32 tcgen05 cta_group::2 + fused top-c)"),
-        "achieved": achieved, "peak": tf32_peak / 3.0, "unit": "TFLOP/s",
-        "frac": achieved / (tf32_peak / 3.0), "traffic": None,
-        "issued_tf32_tflops": 3.0 * achieved, "tf32_peak": tf32_peak,
-        "peak_source": f"{peaks['source']} bf16_tflops_sustained / 2 (TF32 rate) / 3 (3xTF32 "
-                       "issues 3 MMAs per algorithmic MAC)",
+        "kernel": kernel_names[kind],
+        "achieved": achieved, "peak": tf32_peak / mmas, "unit": "TFLOP/s",
+        "frac": achieved / (tf32_peak / mmas), "traffic": None,
+        "issued_tf32_tflops": mmas * achieved, "tf32_peak": tf32_peak,
+        "peak_source": f"{peaks['source']} bf16_tflops_sustained / 2 (TF32 rate)" +
+                       (" / 3 (3xTF32 issues 3 MMAs per algorithmic MAC)" if mmas == 3.0 else ""),
         "launches": top_n, "avg_launch_ms": (top_ms / top_n) if top_n else None,
         "kernel_share_of_step": (top_ms / ms) if ms else None,
         "all_search_launches_share_of_step": (search_ms / ms) if ms else None,
         "algorithmic_flop_per_launch": top_flop, "search_launches": detail,
-        "dual_direction": fused_stats,
+        "dual_direction": fused_stats, "screen": search_stats,
     }
     if rank == 0:
         try:
@@ -398,10 +411,11 @@ def run_b200(args, w):
         line = {
             "metric": "queries_per_s", "value": value, "unit": "queries/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "tf32x3",
-            "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "tf32" if kind.startswith("screen") else "tf32x3", "data": "synthetic",
             "config": {"workload": w["name"], "l2": "inputs (>=1 GB) exceed the 126 MB L2",
                        "search_impl": args.search_impl, "fused": args.fused,
+                       "precision": args.precision,
                        "hub_scores": not args.no_hub_scores,
                        "parallelism": f"index rows sharded over {world} GPU(s), NCCL all-gather + "
                                       "merge kernel" if world > 1 else "single GPU"},

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define KB2_VERSION 1
+#define KB2_VERSION 2
 
 /* metric codes (kiez SklearnNN metric names; minkowski/l2 are p=2 euclidean) */
 #define KB2_METRIC_EUCLIDEAN   0
@@ -104,9 +104,42 @@ int kb2_knn_fused(const float *x_hi, const float *x_lo, const float *x_key, int6
                   int dpad, int cap, int splits, const float *tau_col, uint32_t *col_cnt,
                   uint64_t *col_buf, int col_cap, int32_t *cand_idx, void *stream);
 /* Per column: the cap emitted rows with the smallest column keys -> cand_idx [ny][cap]
- * (-1 padded), overflow[col] = 1 if more than col_cap rows were emitted. */
+ * (-1 padded), overflow[col] = 1 if more than col_cap rows were emitted.  Optional (both or
+ * neither): tau_col = the thresholds the pass ran with, col_tau [ny] out = a lower bound of
+ * the column key of every row that was NOT kept (input of kb2_refine_topk_checked). */
 int kb2_col_select(const uint64_t *col_buf, const uint32_t *col_cnt, int64_t ny, int col_cap,
-                   int cap, int32_t *cand_idx, int32_t *overflow, void *stream);
+                   int cap, int32_t *cand_idx, int32_t *overflow, const float *tau_col,
+                   float *col_tau, void *stream);
+
+/*
+ * Screening candidate search (knn_screen.cu): same contract as kb2_knn_candidates /
+ * kb2_knn_fused, but the keys come from ONE TF32 product (the hi halves only) -- 3x fewer
+ * MMAs, and the 128 x dpad query tile stays resident in shared memory.  Its candidate lists
+ * are proposals: kb2_refine_topk_checked proves per row that the exact top k lies inside the
+ * list and flags the rows where the proof fails, which the caller searches again with
+ * kb2_knn_candidates (3xTF32).  Results are therefore the same as with the 3xTF32 search.
+ *   steps/chained from kb2_screen_plan: the index is cut into `steps` contiguous ranges;
+ *     chained = 1: ranges are sized for L2, searched in order per query tile, the lists are
+ *       carried from range to range -> cand_idx/cand_key [nq][cap]; needs
+ *       chain_flag [ceil(nq/128)*4] int32 scratch (zeroed by the call)
+ *     chained = 0: independent ranges -> cand_idx/cand_key [nq][steps*cap]
+ *   cand_key is required (fp32 screen keys, ascending per list, +inf padded): the last key of
+ *     a list is the tau of the proof.
+ *   dual-direction form when tau_col != NULL: additionally appends to col_buf/col_cnt like
+ *     kb2_knn_fused (q_key = the row-side selection terms).
+ * kb2_screen_stages: pipeline stages the kernel gets for (dpad, cap); 0 = shape not
+ *   supported (dpad > 256 or lists too long for the shared memory left by the query tile).
+ */
+int kb2_screen_stages(int dpad, int cap, int dual);
+int kb2_screen_plan(int64_t nq, int64_t ny, int dpad, int cap, int sm_count, int *steps,
+                    int *chained);
+int kb2_knn_screen(const float *q_hi, const float *q_key, int64_t nq, const float *y_hi,
+                   const float *y_key, int64_t ny, int dpad, int cap, int steps, int chained,
+                   int32_t *cand_idx, float *cand_key, int32_t *chain_flag, const float *tau_col,
+                   uint32_t *col_cnt, uint64_t *col_buf, int col_cap, void *stream);
+/* max(0, max_i x[i]) -> *out (device): the largest selection term ||y - center||^2 of an
+ * index, input of the completeness proof. */
+int kb2_max_f32(const float *x, int64_t n, float *out, void *stream);
 
 /*
  * Exact finish -- recomputes the distance of every candidate in float64 from
@@ -128,6 +161,27 @@ int kb2_refine_topk(const void *q, int64_t nq, int64_t ldq, const void *y, int64
                     const double *y_sqnorm, const int32_t *cand_idx, int ncand, int metric,
                     int64_t index_base, int exclude_self, int64_t self_offset, int k,
                     double *out_dist, int64_t *out_ind, void *stream);
+
+/*
+ * Exact finish + completeness proof for lists proposed by kb2_knn_screen.  Same outputs as
+ * kb2_refine_topk; additionally unverified[row] = 0 when the float64 k-th best distance
+ * proves that no index row outside the list can be among the k nearest, else 1:
+ *   every non-candidate has screen key >= tau_row = min_j tau[row*tau_row_stride + j*tau_step],
+ *   j < tau_count (+inf = the list never filled: nothing was left out);
+ *   |screen key - exact key| <= E(eps_dot, ||q-c||, max ||y-c||);  verified iff
+ *   exact key of the k-th best < tau_row - E.
+ *   q_key [nq] / y_key_max (device scalar): selection terms of the queries / their maximum
+ *   over the index (kb2_max_f32); ignored for cosine (unit rows).
+ *   eps_dot: relative bound of the screen's dot-product error, 2^-10 (1 + 2^-9) + dpad 2^-23 + 2^-21.
+ */
+int kb2_refine_topk_checked(const void *q, int64_t nq, int64_t ldq, const void *y, int64_t ny,
+                            int64_t ldy, int d, int elem_size, const double *q_sqnorm,
+                            const double *y_sqnorm, const int32_t *cand_idx, int ncand,
+                            int metric, int64_t index_base, int exclude_self,
+                            int64_t self_offset, int k, double *out_dist, int64_t *out_ind,
+                            const float *tau, int64_t tau_row_stride, int tau_step,
+                            int tau_count, const float *q_key, const float *y_key_max,
+                            double eps_dot, int32_t *unverified, void *stream);
 
 /*
  * Row-wise top-k of (dist, ind) pairs, ascending, ties by input position, NaN last.

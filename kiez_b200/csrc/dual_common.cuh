@@ -1,0 +1,116 @@
+// Column side of the dual-direction kernels (knn_fused.cu: 3xTF32, knn_screen.cu: 1xTF32
+// screen): every accumulator element whose column key  x_key[row] - 2 <x,y>  beats the
+// column's threshold tau_col[col] is appended to that column's buffer in global memory.
+#pragma once
+#include "tc_common.cuh"
+
+namespace kb2 {
+
+constexpr int EMIT_Q = 48;       // pending emits per column-epilogue warp; flushed above 16
+constexpr int EMIT_WORDS = 4 * EMIT_Q * 2 + 4 * EMIT_Q / 4;   // floats: keys + cols + lanes(bytes)
+
+struct FusedParams {
+    const float *x_key;          // [nq] row-side selection term
+    const float *tau_col;        // [ny]
+    unsigned int *col_cnt;       // [ny] rows emitted so far (may exceed col_cap: overflow)
+    ent_t *col_buf;              // [ny][col_cap] packed (column key, row)
+    int col_cap;
+};
+
+// The emit queue of one column-epilogue warp (shared memory).
+struct EmitQueue {
+    float *key;
+    int *col;
+    unsigned char *lane;
+    int n;                       // pending emits (warp-uniform)
+};
+
+// Drain up to 32 pending emits of a warp: lane i claims a slot of its entry's column buffer
+// (32 independent atomics in flight) and writes (column key, row); the rest moves down.
+__device__ __forceinline__ void emit_flush(const FusedParams &FP, EmitQueue &Q, int64_t row_base,
+                                           int lane) {
+    __syncwarp();
+    const int take = min(Q.n, 32);
+    float key = 0.f;
+    int col = 0, owner = 0;
+    if (lane < take) { key = Q.key[lane]; col = Q.col[lane]; owner = Q.lane[lane]; }
+    float key2 = 0.f;
+    int col2 = 0, owner2 = 0;
+    const bool more = lane + 32 < Q.n;
+    if (more) { key2 = Q.key[lane + 32]; col2 = Q.col[lane + 32]; owner2 = Q.lane[lane + 32]; }
+    if (lane < take) {
+        const unsigned int pos = atomicAdd(FP.col_cnt + col, 1u);
+        if (pos < (unsigned int)FP.col_cap)
+            FP.col_buf[(size_t)col * FP.col_cap + pos] = pack_entry(key, (int)(row_base + owner));
+    }
+    __syncwarp();
+    if (more) { Q.key[lane] = key2; Q.col[lane] = col2; Q.lane[lane] = (unsigned char)owner2; }
+    __syncwarp();
+    Q.n -= take;
+}
+
+// tau_col[c0 .. c0+BN) -> registers, lane l holds columns t*32 + l; -inf masks a column.
+template <int BN>
+__device__ __forceinline__ void load_taucol(const float *__restrict__ tau_col, int64_t c0,
+                                            int64_t y_end, int lane, float (&treg)[BN / 32]) {
+#pragma unroll
+    for (int t = 0; t < BN / 32; ++t) {
+        const int64_t col = c0 + t * 32 + lane;
+        treg[t] = (col < y_end) ? __ldg(tau_col + col) : -INFINITY;
+    }
+}
+
+// One accumulator tile (this warp's 32 TMEM lanes x BN columns), column side.
+// `tk` = this warp's shared copy of the tile's thresholds, xk = x_key of this thread's row
+// (+inf for rows that do not exist: they never emit), row_base = row of lane 0.
+template <int BN>
+__device__ __forceinline__ void column_tile(const FusedParams &FP, EmitQueue &Q, const float *tk,
+                                            uint32_t taddr, int64_t c0, float xk, int64_t row_base,
+                                            int lane) {
+    const float nxk = -xk;
+#pragma unroll 1
+    for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + ch * 32, r);
+        tmem_ld_wait();
+        // g = -2 acc - tau_col;  emit when  key_x - 2 acc < tau_col  <=>  g < -key_x
+        float g[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) g[j] = fmaf(-2.f, __uint_as_float(r[j]), -tk[ch * 32 + j]);
+        float m4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            m4[q] = g[8 * q];
+#pragma unroll
+            for (int j = 1; j < 8; ++j) m4[q] = fminf(m4[q], g[8 * q + j]);
+        }
+        const float gmin = fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
+        if (!__any_sync(FULL_MASK, gmin < nxk)) continue;
+        // Survivors go to the warp's queue (ballot-ranked, no atomics); the queue is drained
+        // 17-48 entries at a time so that the global atomics that assign the column-buffer
+        // slots are in flight together instead of one latency each.
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            bool any_pass = false;
+#pragma unroll
+            for (int j = 4 * q; j < 4 * q + 4; ++j) any_pass |= (g[j] < nxk);
+            if (!__any_sync(FULL_MASK, any_pass)) continue;
+#pragma unroll
+            for (int j = 4 * q; j < 4 * q + 4; ++j) {
+                const bool pass = g[j] < nxk;
+                const unsigned mask = __ballot_sync(FULL_MASK, pass);
+                if (mask == 0) continue;
+                if (pass) {
+                    const int slot = Q.n + __popc(mask & ((1u << lane) - 1));
+                    Q.key[slot] = fmaf(-2.f, __uint_as_float(r[j]), xk);
+                    Q.col[slot] = (int)(c0 + ch * 32 + j);
+                    Q.lane[slot] = (unsigned char)lane;
+                }
+                Q.n += __popc(mask);
+                if (Q.n > EMIT_Q - 32) emit_flush(FP, Q, row_base, lane);
+            }
+        }
+    }
+}
+
+}  // namespace kb2

@@ -18,47 +18,13 @@
 //              TMEM lane quadrant of warp w), threshold test, atomic append
 //   warp  8    TMA producer, warp 9 MMA issuer (CTA 0), warps 10-11 idle
 // tmem_empty therefore collects 8 warps x 2 CTAs.
-#include "tc_common.cuh"
+#include "dual_common.cuh"
 
 namespace kb2 {
 
 constexpr int F_THREADS = 384;
-constexpr int EMIT_Q = 48;       // pending emits per column-epilogue warp; flushed above 16
-constexpr int EMIT_WORDS = 4 * EMIT_Q * 2 + 4 * EMIT_Q / 4;   // floats: keys + cols + lanes(bytes)
 constexpr int F_BN = 256;        // index (column) rows per tile of the CTA pair
 constexpr int F_HALF = 128;
-
-struct FusedParams {
-    const float *x_key;          // [nq] row-side selection term
-    const float *tau_col;        // [ny]
-    unsigned int *col_cnt;       // [ny] rows emitted so far (may exceed col_cap: overflow)
-    ent_t *col_buf;              // [ny][col_cap] packed (column key, row)
-    int col_cap;
-};
-
-// Drain up to 32 pending emits of a warp: lane i claims a slot of its entry's column buffer
-// (32 independent atomics in flight) and writes (column key, row); the rest moves down.
-__device__ __forceinline__ int emit_flush(const FusedParams &FP, float *qkey, int *qcol,
-                                          unsigned char *qlane, int qn, int64_t row_base, int lane) {
-    __syncwarp();
-    const int take = min(qn, 32);
-    float key = 0.f;
-    int col = 0, owner = 0;
-    if (lane < take) { key = qkey[lane]; col = qcol[lane]; owner = qlane[lane]; }
-    float key2 = 0.f;
-    int col2 = 0, owner2 = 0;
-    const bool more = lane + 32 < qn;
-    if (more) { key2 = qkey[lane + 32]; col2 = qcol[lane + 32]; owner2 = qlane[lane + 32]; }
-    if (lane < take) {
-        const unsigned int pos = atomicAdd(FP.col_cnt + col, 1u);
-        if (pos < (unsigned int)FP.col_cap)
-            FP.col_buf[(size_t)col * FP.col_cap + pos] = pack_entry(key, (int)(row_base + owner));
-    }
-    __syncwarp();
-    if (more) { qkey[lane] = key2; qcol[lane] = col2; qlane[lane] = (unsigned char)owner2; }
-    __syncwarp();
-    return qn - take;
-}
 
 template <int BK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1)
@@ -259,10 +225,11 @@ knn_fused_kernel(const __grid_constant__ CUtensorMap map_q_hi,
         const int quad = warp - 4;                         // TMEM lane quadrant
         const int lrow = quad * 32 + lane;
         float *tk = tile_s + warp * BN;                    // this warp's tau_col tile
-        float *qkey = emit_key + quad * EMIT_Q;
-        int *qcol = emit_col + quad * EMIT_Q;
-        unsigned char *qlane = emit_lane + quad * EMIT_Q;
-        int qn = 0;                                        // pending emits (warp-uniform)
+        EmitQueue Q;
+        Q.key = emit_key + quad * EMIT_Q;
+        Q.col = emit_col + quad * EMIT_Q;
+        Q.lane = emit_lane + quad * EMIT_Q;
+        Q.n = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int64_t u = pair_id; u < num_units; u += num_pairs) {
@@ -273,77 +240,25 @@ knn_fused_kernel(const __grid_constant__ CUtensorMap map_q_hi,
             const int64_t grow = qt * BM + lrow;
             // rows that do not exist never emit: -xk = -inf
             const float xk = (grow < P.nq) ? __ldg(FP.x_key + grow) : INFINITY;
-            const float nxk = -xk;
             const int64_t row_base = qt * BM + quad * 32;  // row of lane 0 of this warp
             float treg[BN / 32];
-#pragma unroll
-            for (int t = 0; t < BN / 32; ++t) {
-                const int64_t col = y_begin + t * 32 + lane;
-                treg[t] = (col < y_end) ? __ldg(FP.tau_col + col) : -INFINITY;   // -inf masks the column
-            }
+            load_taucol<BN>(FP.tau_col, y_begin, y_end, lane, treg);
             for (int64_t c0 = y_begin; c0 < y_end; c0 += BN) {
                 __syncwarp();
 #pragma unroll
                 for (int t = 0; t < BN / 32; ++t) tk[t * 32 + lane] = treg[t];
                 __syncwarp();
-#pragma unroll
-                for (int t = 0; t < BN / 32; ++t) {
-                    const int64_t col = c0 + BN + t * 32 + lane;
-                    treg[t] = (col < y_end) ? __ldg(FP.tau_col + col) : -INFINITY;
-                }
+                load_taucol<BN>(FP.tau_col, c0 + BN, y_end, lane, treg);
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-                for (int ch = 0; ch < BN / 32; ++ch) {
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(taddr + ch * 32, r);
-                    tmem_ld_wait();
-                    // g = -2 acc - tau_col;  emit when  key_x - 2 acc < tau_col  <=>  g < -key_x
-                    float g[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        g[j] = fmaf(-2.f, __uint_as_float(r[j]), -tk[ch * 32 + j]);
-                    float m4[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        m4[q] = g[8 * q];
-#pragma unroll
-                        for (int j = 1; j < 8; ++j) m4[q] = fminf(m4[q], g[8 * q + j]);
-                    }
-                    const float gmin = fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
-                    if (!__any_sync(FULL_MASK, gmin < nxk)) continue;
-                    // Survivors go to the warp's queue (ballot-ranked, no atomics); the queue is
-                    // drained 17-48 entries at a time so that the global atomics that assign the
-                    // column-buffer slots are in flight together instead of one latency each.
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        bool any_pass = false;
-#pragma unroll
-                        for (int j = 4 * q; j < 4 * q + 4; ++j) any_pass |= (g[j] < nxk);
-                        if (!__any_sync(FULL_MASK, any_pass)) continue;
-#pragma unroll
-                        for (int j = 4 * q; j < 4 * q + 4; ++j) {
-                            const bool pass = g[j] < nxk;
-                            const unsigned mask = __ballot_sync(FULL_MASK, pass);
-                            if (mask == 0) continue;
-                            if (pass) {
-                                const int slot = qn + __popc(mask & ((1u << lane) - 1));
-                                qkey[slot] = fmaf(-2.f, __uint_as_float(r[j]), xk);
-                                qcol[slot] = (int)(c0 + ch * 32 + j);
-                                qlane[slot] = (unsigned char)lane;
-                            }
-                            qn += __popc(mask);
-                            if (qn > EMIT_Q - 32) qn = emit_flush(FP, qkey, qcol, qlane, qn, row_base, lane);
-                        }
-                    }
-                }
+                column_tile<BN>(FP, Q, tk, taddr, c0, xk, row_base, lane);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(tmem_empty_leader + (uint32_t)acc * 8);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            while (qn > 0) qn = emit_flush(FP, qkey, qcol, qlane, qn, row_base, lane);   // rows change with the unit
+            while (Q.n > 0) emit_flush(FP, Q, row_base, lane);   // rows change with the unit
         }
     }
 
@@ -363,7 +278,8 @@ constexpr int CS_WARPS = 4;
 __global__ void __launch_bounds__(CS_WARPS * 32)
 col_select_kernel(const ent_t *__restrict__ col_buf, const unsigned int *__restrict__ col_cnt,
                   int64_t ny, int col_cap, int P2, int cap, int32_t *__restrict__ cand_idx,
-                  int32_t *__restrict__ overflow) {
+                  int32_t *__restrict__ overflow, const float *__restrict__ tau_col,
+                  float *__restrict__ col_tau) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     ent_t *e = reinterpret_cast<ent_t *>(smem_raw) + (size_t)warp * P2;
@@ -390,6 +306,9 @@ col_select_kernel(const ent_t *__restrict__ col_buf, const unsigned int *__restr
     }
     __syncwarp();
     for (int p = lane; p < cap; p += 32) cand_idx[col * cap + p] = (p < n) ? entry_col(e[p]) : -1;
+    // every row that was not kept has column key >= col_tau: emitted rows beyond the cap-th
+    // best by the sort, rows never emitted by the threshold test
+    if (col_tau && lane == 0) col_tau[col] = (n >= cap) ? entry_key(e[cap - 1]) : tau_col[col];
 }
 
 static size_t fused_stage_bytes(int bk) { return (size_t)(2 * BM + 2 * F_HALF) * bk * 4; }
@@ -465,8 +384,9 @@ extern "C" int kb2_knn_fused(const float *x_hi, const float *x_lo, const float *
 
 extern "C" int kb2_col_select(const uint64_t *col_buf, const uint32_t *col_cnt, int64_t ny,
                               int col_cap, int cap, int32_t *cand_idx, int32_t *overflow,
-                              void *stream) {
+                              const float *tau_col, float *col_tau, void *stream) {
     KB2_CHECK(ny >= 0 && cap > 0 && col_cap >= cap && col_cap <= 4096, "col_select: bad arguments");
+    KB2_CHECK(!col_tau || tau_col, "col_select: col_tau needs the tau_col the pass ran with");
     if (ny == 0) return 0;
     const int P2 = max(32, next_pow2(col_cap));   // the sort network starts at 32 entries
     const size_t smem = (size_t)CS_WARPS * P2 * sizeof(ent_t);
@@ -474,7 +394,7 @@ extern "C" int kb2_col_select(const uint64_t *col_buf, const uint32_t *col_cnt, 
                                   (int)smem));
     col_select_kernel<<<(unsigned)ceil_div64(ny, CS_WARPS), CS_WARPS * 32, smem,
                         (cudaStream_t)stream>>>(reinterpret_cast<const ent_t *>(col_buf), col_cnt, ny,
-                                                col_cap, P2, cap, cand_idx, overflow);
+                                                col_cap, P2, cap, cand_idx, overflow, tau_col, col_tau);
     KB2_LAUNCH_CHECK();
     return 0;
 }

@@ -52,7 +52,31 @@ prepare_rows_kernel(const float *__restrict__ x, int64_t n, int d, int64_t ldx,
     }
 }
 
+// max(0, max_i x[i]) of non-negative selection terms: the bit patterns of non-negative floats
+// order like unsigned integers.
+__global__ void __launch_bounds__(256)
+max_f32_kernel(const float *__restrict__ x, int64_t n, unsigned int *__restrict__ out) {
+    float m = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, x[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+
 }  // namespace kb2
+
+extern "C" int kb2_max_f32(const float *x, int64_t n, float *out, void *stream) {
+    KB2_CHECK(n >= 0 && out, "max_f32: bad arguments");
+    KB2_CUDA(cudaMemsetAsync(out, 0, sizeof(float), (cudaStream_t)stream));
+    if (n == 0) return 0;
+    const int64_t blocks = kb2::ceil_div64(n, 256 * 8);
+    kb2::max_f32_kernel<<<(unsigned)(blocks > 1184 ? 1184 : blocks), 256, 0, (cudaStream_t)stream>>>(
+        x, n, reinterpret_cast<unsigned int *>(out));
+    KB2_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int kb2_padded_dim(int d) { return ((d + 31) / 32) * 32; }
 

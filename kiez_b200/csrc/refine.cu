@@ -6,17 +6,38 @@ namespace kb2 {
 
 constexpr int REFINE_WARPS = 4;
 
+// Completeness proof for candidate lists that come from the 1xTF32 screen (knn_screen.cu).
+// Every index row NOT in the list has screen key >= tau (the list's cap-th best screen key;
+// the minimum over the lists when the index was searched in independent ranges), and
+//   |screen key - exact key| <= E = 2 eps_dot ||q-c|| ||y-c||_max + 2^-21 (||y-c||^2_max + 2 ||q-c|| ||y-c||_max)
+// (TF32 rounding of both operands <= 2^-11 each, fp32 accumulation, fp32 key terms), where
+//   exact key = d^2(q, y) - ||q-c||^2     (euclidean metrics, c = the centring vector)
+//             = 2 (cosine distance - 1)   (cosine: rows are normalised, norms are 1).
+// So if the exact k-th best distance satisfies  key_k < tau - E  no outside row can belong to
+// the k nearest and the result is exact; otherwise unverified[row] = 1 and the caller
+// searches that row again with the 3xTF32 kernel.
+struct CheckParams {
+    const float *tau;          // first tau of row 0
+    int64_t tau_row_stride;    // elements between rows
+    int tau_step, tau_count;   // tau_count values per row, tau_step elements apart
+    const float *q_key;        // [nq] fp32 ||q-c||^2 (unused for cosine)
+    const float *y_key_max;    // device scalar: max ||y-c||^2 over the index (unused for cosine)
+    double eps_dot;            // bound of |screen dot - exact dot| / (||q-c|| ||y-c||)
+    int32_t *unverified;       // [nq] out
+};
+
 // One warp per query row: gather each candidate's raw fp32 row, accumulate the
 // distance in fp64, then bitonic-sort (dist, id) in shared memory and write the
 // best k.  HBM/L2-bound on the row gathers (ncand * d * 4 B per query).
-template <typename T, bool VEC4>
+template <typename T, bool VEC4, bool CHECK>
 __global__ void __launch_bounds__(REFINE_WARPS * 32)
 refine_topk_kernel(const T *__restrict__ q, int64_t nq, int64_t ldq,
                    const T *__restrict__ y, int64_t ny, int64_t ldy, int d,
                    const double *__restrict__ q_sqnorm, const double *__restrict__ y_sqnorm,
                    const int32_t *__restrict__ cand_idx, int ncand, int P, int metric,
                    int64_t index_base, int exclude_self, int64_t self_offset, int k,
-                   double *__restrict__ out_dist, int64_t *__restrict__ out_ind) {
+                   double *__restrict__ out_dist, int64_t *__restrict__ out_ind,
+                   const CheckParams CP) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *key = reinterpret_cast<double *>(smem_raw) + (size_t)warp * P;
@@ -79,6 +100,30 @@ refine_topk_kernel(const T *__restrict__ q, int64_t nq, int64_t ldq,
         out_dist[row * k + j] = key[j];
         out_ind[row * k + j] = (tie[j] == INT64_MAX) ? -1 : tie[j];
     }
+    if constexpr (CHECK) {
+        if (lane == 0) {
+            float tau = INFINITY;
+            for (int j = 0; j < CP.tau_count; ++j)
+                tau = fminf(tau, CP.tau[row * CP.tau_row_stride + (int64_t)j * CP.tau_step]);
+            const double kd = key[k - 1];          // exact k-th best distance (+inf: fewer than k)
+            bool ok;
+            if (tau == INFINITY) {
+                ok = true;                         // lists not full: every index row is a candidate
+            } else if (!(kd < INFINITY)) {
+                ok = false;
+            } else if (metric == KB2_METRIC_COSINE) {
+                const double E = 2.0 * CP.eps_dot * 1.000001 + 1e-6;
+                ok = 2.0 * (kd - 1.0) + 1e-9 < (double)tau - E;
+            } else {
+                const double d2 = (metric == KB2_METRIC_EUCLIDEAN) ? kd * kd : kd;
+                const double qn2 = (double)CP.q_key[row], ym2 = (double)*CP.y_key_max;
+                const double qn = sqrt(qn2) * 1.000001, ym = sqrt(ym2) * 1.000001;
+                const double E = 2.0 * CP.eps_dot * qn * ym + 4.76837158203125e-07 * (ym2 + 2.0 * qn * ym);
+                ok = d2 * (1.0 + 1e-12) < (double)tau - E + qn2 * (1.0 - 2.4e-7);
+            }
+            CP.unverified[row] = ok ? 0 : 1;
+        }
+    }
 }
 
 // Row-wise top-k of (dist, ind): one warp per row, bitonic sort in smem keyed by
@@ -122,29 +167,30 @@ int launch_topk_rows_rg(const double *, const int64_t *, int64_t, int, int, int6
 
 }  // namespace kb2
 
-template <typename T, bool VEC4>
+template <typename T, bool VEC4, bool CHECK>
 static int launch_refine(const void *q, int64_t nq, int64_t ldq, const void *y, int64_t ny,
                          int64_t ldy, int d, const double *q_sqnorm, const double *y_sqnorm,
                          const int32_t *cand_idx, int ncand, int P, int metric, int64_t index_base,
                          int exclude_self, int64_t self_offset, int k, double *out_dist,
-                         int64_t *out_ind, cudaStream_t st) {
+                         int64_t *out_ind, const kb2::CheckParams &CP, cudaStream_t st) {
     using namespace kb2;
     const size_t smem = (size_t)REFINE_WARPS * P * 16;
-    KB2_CUDA(cudaFuncSetAttribute(refine_topk_kernel<T, VEC4>,
+    KB2_CUDA(cudaFuncSetAttribute(refine_topk_kernel<T, VEC4, CHECK>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    refine_topk_kernel<T, VEC4><<<(unsigned)ceil_div64(nq, REFINE_WARPS), REFINE_WARPS * 32, smem, st>>>(
+    refine_topk_kernel<T, VEC4, CHECK><<<(unsigned)ceil_div64(nq, REFINE_WARPS), REFINE_WARPS * 32, smem, st>>>(
         static_cast<const T *>(q), nq, ldq, static_cast<const T *>(y), ny, ldy, d, q_sqnorm, y_sqnorm,
-        cand_idx, ncand, P, metric, index_base, exclude_self, self_offset, k, out_dist, out_ind);
+        cand_idx, ncand, P, metric, index_base, exclude_self, self_offset, k, out_dist, out_ind, CP);
     KB2_LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int kb2_refine_topk(const void *q, int64_t nq, int64_t ldq, const void *y, int64_t ny,
-                               int64_t ldy, int d, int elem_size, const double *q_sqnorm,
-                               const double *y_sqnorm, const int32_t *cand_idx, int ncand,
-                               int metric, int64_t index_base, int exclude_self,
-                               int64_t self_offset, int k, double *out_dist, int64_t *out_ind,
-                               void *stream) {
+template <bool CHECK>
+static int refine_dispatch(const void *q, int64_t nq, int64_t ldq, const void *y, int64_t ny,
+                           int64_t ldy, int d, int elem_size, const double *q_sqnorm,
+                           const double *y_sqnorm, const int32_t *cand_idx, int ncand, int metric,
+                           int64_t index_base, int exclude_self, int64_t self_offset, int k,
+                           double *out_dist, int64_t *out_ind, const kb2::CheckParams &CP,
+                           cudaStream_t st) {
     using namespace kb2;
     KB2_CHECK(nq >= 0 && ny > 0 && d > 0 && ldq >= d && ldy >= d, "refine_topk: bad shape");
     KB2_CHECK(elem_size == 4 || elem_size == 8, "refine_topk: elem_size must be 4 (fp32) or 8 (fp64)");
@@ -155,18 +201,51 @@ extern "C" int kb2_refine_topk(const void *q, int64_t nq, int64_t ldq, const voi
               "refine_topk: cosine needs q_sqnorm and y_sqnorm");
     if (nq == 0) return 0;
     const int P = next_pow2(ncand);
-    cudaStream_t st = (cudaStream_t)stream;
     if (elem_size == 8)
-        return launch_refine<double, false>(q, nq, ldq, y, ny, ldy, d, q_sqnorm, y_sqnorm, cand_idx,
-                                            ncand, P, metric, index_base, exclude_self, self_offset, k, out_dist, out_ind, st);
+        return launch_refine<double, false, CHECK>(q, nq, ldq, y, ny, ldy, d, q_sqnorm, y_sqnorm, cand_idx,
+                                                   ncand, P, metric, index_base, exclude_self, self_offset, k, out_dist, out_ind, CP, st);
     const bool vec = (d % 4 == 0) && (ldq % 4 == 0) && (ldy % 4 == 0) &&
                      ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(y)) % 16 == 0);
     if (vec)
-        return launch_refine<float, true>(q, nq, ldq, y, ny, ldy, d, q_sqnorm, y_sqnorm, cand_idx,
-                                          ncand, P, metric, index_base, exclude_self, self_offset, k, out_dist, out_ind, st);
-    return launch_refine<float, false>(q, nq, ldq, y, ny, ldy, d, q_sqnorm, y_sqnorm, cand_idx, ncand,
-                                       P, metric, index_base, exclude_self, self_offset, k, out_dist,
-                                       out_ind, st);
+        return launch_refine<float, true, CHECK>(q, nq, ldq, y, ny, ldy, d, q_sqnorm, y_sqnorm, cand_idx,
+                                                 ncand, P, metric, index_base, exclude_self, self_offset, k, out_dist, out_ind, CP, st);
+    return launch_refine<float, false, CHECK>(q, nq, ldq, y, ny, ldy, d, q_sqnorm, y_sqnorm, cand_idx, ncand,
+                                              P, metric, index_base, exclude_self, self_offset, k, out_dist,
+                                              out_ind, CP, st);
+}
+
+extern "C" int kb2_refine_topk(const void *q, int64_t nq, int64_t ldq, const void *y, int64_t ny,
+                               int64_t ldy, int d, int elem_size, const double *q_sqnorm,
+                               const double *y_sqnorm, const int32_t *cand_idx, int ncand,
+                               int metric, int64_t index_base, int exclude_self,
+                               int64_t self_offset, int k, double *out_dist, int64_t *out_ind,
+                               void *stream) {
+    kb2::CheckParams CP = {};
+    return refine_dispatch<false>(q, nq, ldq, y, ny, ldy, d, elem_size, q_sqnorm, y_sqnorm, cand_idx,
+                                  ncand, metric, index_base, exclude_self, self_offset, k, out_dist,
+                                  out_ind, CP, (cudaStream_t)stream);
+}
+
+extern "C" int kb2_refine_topk_checked(const void *q, int64_t nq, int64_t ldq, const void *y,
+                                       int64_t ny, int64_t ldy, int d, int elem_size,
+                                       const double *q_sqnorm, const double *y_sqnorm,
+                                       const int32_t *cand_idx, int ncand, int metric,
+                                       int64_t index_base, int exclude_self, int64_t self_offset,
+                                       int k, double *out_dist, int64_t *out_ind, const float *tau,
+                                       int64_t tau_row_stride, int tau_step, int tau_count,
+                                       const float *q_key, const float *y_key_max, double eps_dot,
+                                       int32_t *unverified, void *stream) {
+    using namespace kb2;
+    KB2_CHECK(tau && unverified && tau_count >= 1, "refine_topk_checked: tau and unverified are required");
+    KB2_CHECK(metric == KB2_METRIC_COSINE || (q_key && y_key_max),
+              "refine_topk_checked: euclidean metrics need q_key and y_key_max");
+    KB2_CHECK(eps_dot > 0.0 && eps_dot < 100.0, "refine_topk_checked: eps_dot=%g out of range", eps_dot);
+    CheckParams CP;
+    CP.tau = tau; CP.tau_row_stride = tau_row_stride; CP.tau_step = tau_step; CP.tau_count = tau_count;
+    CP.q_key = q_key; CP.y_key_max = y_key_max; CP.eps_dot = eps_dot; CP.unverified = unverified;
+    return refine_dispatch<true>(q, nq, ldq, y, ny, ldy, d, elem_size, q_sqnorm, y_sqnorm, cand_idx,
+                                 ncand, metric, index_base, exclude_self, self_offset, k, out_dist,
+                                 out_ind, CP, (cudaStream_t)stream);
 }
 
 extern "C" int kb2_topk_rows(const double *dist, const int64_t *ind, int64_t n, int c, int nparts,

@@ -150,10 +150,11 @@ class PreparedRows:
     """Device-resident operands of one embedding matrix: the raw fp32 rows (exact
     finish), their 3xTF32 split and selection term (candidate search)."""
 
-    __slots__ = ("raw", "hi", "lo", "key", "sqnorm", "n", "d", "dpad", "base", "_owner")
+    __slots__ = ("raw", "hi", "lo", "key", "sqnorm", "keymax", "n", "d", "dpad", "base", "_owner")
 
-    def __init__(self, raw, hi, lo, key, sqnorm, base=0, owner=None):
+    def __init__(self, raw, hi, lo, key, sqnorm, base=0, owner=None, keymax=None):
         self.raw, self.hi, self.lo, self.key, self.sqnorm = raw, hi, lo, key, sqnorm
+        self.keymax = keymax    # device scalar >= max(key): input of the screen's completeness proof
         self.n, self.d = raw.shape
         self.dpad = hi.shape[1]
         self.base = base        # global id of row 0 (multi-GPU shards)
@@ -164,13 +165,13 @@ class PreparedRows:
         return PreparedRows(self.raw.index_select(0, idx), self.hi.index_select(0, idx),
                             self.lo.index_select(0, idx), self.key.index_select(0, idx),
                             None if self.sqnorm is None else self.sqnorm.index_select(0, idx),
-                            base=0, owner=self._owner)
+                            base=0, owner=self._owner, keymax=self.keymax)
 
     def rows(self, lo, hi):
         """A contiguous row shard (views, no copy)."""
         return PreparedRows(self.raw[lo:hi], self.hi[lo:hi], self.lo[lo:hi], self.key[lo:hi],
                             None if self.sqnorm is None else self.sqnorm[lo:hi],
-                            base=self.base + lo, owner=self._owner)
+                            base=self.base + lo, owner=self._owner, keymax=self.keymax)
 
 
 def candidate_capacity(c: int) -> int:
@@ -187,7 +188,8 @@ class B200Mixin:
 
     def __init__(self, n_candidates: int = 5, metric: str = "euclidean", p: int = 2,
                  device: Optional[Any] = None, impl: str = "auto", center: bool = True,
-                 distributed: Optional[bool] = None, fused: Any = "auto", n_jobs=None):
+                 distributed: Optional[bool] = None, fused: Any = "auto",
+                 precision: str = "auto", n_jobs=None):
         if torch is None or not torch.cuda.is_available():
             raise ImportError(
                 "The B200 backend needs PyTorch with a CUDA device (sm_100a); there is no "
@@ -201,9 +203,13 @@ class B200Mixin:
             raise ValueError("B200 is an exact contraction backend: minkowski needs p=2")
         if impl not in ("auto", "tc", "tc1", "simt"):
             raise ValueError(f"impl must be 'auto', 'tc', 'tc1' or 'simt', got {impl!r}")
+        if precision not in ("auto", "tf32x3", "screen"):
+            raise ValueError(f"precision must be 'auto', 'tf32x3' or 'screen', got {precision!r}")
         super().__init__(n_candidates=n_candidates, metric=metric, n_jobs=n_jobs)
         self.p = p
         self.impl = impl
+        self.precision = precision
+        self.search_stats = {"screen_rows": 0, "screen_unverified": 0}
         self.center = center
         self._lib = _lib
         self._metric_code = _METRIC_CODES[metric]
@@ -317,10 +323,106 @@ class B200Mixin:
                          lib.stream_ptr())
                 if cosine and raw.dtype == torch.float64:
                     sqn = (raw * raw).sum(dim=1)      # exact norms of the float64 rows
-        prep = PreparedRows(raw, hi, lo, key, sqn, owner=data)
+            keymax = torch.empty((1,), dtype=torch.float32, device=self.device)
+            lib.call("kb2_max_f32", lib.ptr(key), n, lib.ptr(keymax), lib.stream_ptr())
+        prep = PreparedRows(raw, hi, lo, key, sqn, owner=data, keymax=keymax)
         if cache:
             self._prepared[id(data)] = prep
         return prep
+
+    # -- screen (1xTF32 proposals + completeness proof) ------------------------------
+    def _use_screen(self, q: PreparedRows, y: PreparedRows, cap: int, dual: bool) -> bool:
+        """Whether the candidate search runs as the 1xTF32 screen (knn_screen.cu).  The proof in
+        the exact finish assumes the operands are the caller's fp32 values (float64 callers keep
+        the 3xTF32 search) and needs a full list per row to say anything."""
+        if self.precision == "tf32x3" or self.impl not in ("auto", "tc"):
+            return False
+        if q.raw.dtype != torch.float32 or y.raw.dtype != torch.float32:
+            return False
+        if q.dpad != y.dpad or y.n < 4 * cap or q.n < 1:
+            return False
+        return self._lib.lib.kb2_screen_stages(q.dpad, cap, int(dual)) > 0
+
+    def _eps_dot(self, dpad: int) -> float:
+        """Relative bound of |<hi(q), hi(y)> (fp32 accumulate) - <q, y>| / (|q| |y|): both
+        operands rounded to TF32 (2^-11 each, cross term), fp32 centring, accumulation."""
+        return 2.0 ** -10 * (1 + 2.0 ** -9) + dpad * 2.0 ** -23 + 2.0 ** -21
+
+    def _screen_plan(self, nq: int, ny: int, dpad: int, cap: int):
+        import ctypes as C
+
+        lib = self._lib
+        steps, chained = C.c_int(0), C.c_int(0)
+        sm = torch.cuda.get_device_properties(self.device).multi_processor_count
+        lib.call("kb2_screen_plan", nq, ny, dpad, cap, sm, C.addressof(steps), C.addressof(chained))
+        lib.launch_counter -= 1          # host-only entry point
+        return steps.value, chained.value
+
+    def _screen_search(self, q: PreparedRows, y: PreparedRows, cap: int, dual=None):
+        """Launch the screen: returns (cand [nq][L], keys [nq][L], lists per row)."""
+        lib = self._lib
+        dev = self.device
+        steps, chained = self._screen_plan(q.n, y.n, q.dpad, cap)
+        lists = 1 if chained else steps
+        cand = torch.empty((q.n, lists * cap), dtype=torch.int32, device=dev)
+        ckey = torch.empty((q.n, lists * cap), dtype=torch.float32, device=dev)
+        flag = torch.empty(((q.n + 127) // 128 * 4,), dtype=torch.int32, device=dev) if chained else None
+        prof = getattr(self, "_profile", None)       # bench.py: CUDA events around the searches
+        if prof is not None:
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        if dual is None:
+            lib.call("kb2_knn_screen", lib.ptr(q.hi), None, q.n, lib.ptr(y.hi), lib.ptr(y.key), y.n,
+                     q.dpad, cap, steps, chained, lib.ptr(cand), lib.ptr(ckey), lib.ptr(flag),
+                     None, None, None, 0, lib.stream_ptr())
+        else:
+            tau, col_cnt, col_buf, col_cap = dual
+            lib.call("kb2_knn_screen", lib.ptr(q.hi), lib.ptr(q.key), q.n, lib.ptr(y.hi),
+                     lib.ptr(y.key), y.n, q.dpad, cap, steps, chained, lib.ptr(cand), lib.ptr(ckey),
+                     lib.ptr(flag), lib.ptr(tau), lib.ptr(col_cnt), lib.ptr(col_buf), col_cap,
+                     lib.stream_ptr())
+        if prof is not None:
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record()
+            prof.append((ev0, ev1, q.n, y.n, q.d, "screen-dual" if dual is not None else "screen"))
+        return cand, ckey, lists
+
+    def _refine_checked(self, q: PreparedRows, y: PreparedRows, cand, k: int, exclude_self: bool,
+                        tau, tau_row_stride: int, tau_step: int, tau_count: int):
+        """Exact finish + completeness proof; returns (dist, ind, unverified int32 [nq])."""
+        lib = self._lib
+        dev = self.device
+        out_d = torch.empty((q.n, k), dtype=torch.float64, device=dev)
+        out_i = torch.empty((q.n, k), dtype=torch.int64, device=dev)
+        unverified = torch.empty((q.n,), dtype=torch.int32, device=dev)
+        lib.call("kb2_refine_topk_checked", lib.ptr(q.raw), q.n, q.raw.stride(0), lib.ptr(y.raw), y.n,
+                 y.raw.stride(0), q.d, 4, lib.ptr(q.sqnorm), lib.ptr(y.sqnorm), lib.ptr(cand),
+                 cand.shape[1], self._metric_code, y.base, int(exclude_self), y.base - q.base, k,
+                 lib.ptr(out_d), lib.ptr(out_i), tau, tau_row_stride, tau_step, tau_count,
+                 lib.ptr(q.key), lib.ptr(y.keymax), self._eps_dot(q.dpad), lib.ptr(unverified),
+                 lib.stream_ptr())
+        return out_d, out_i, unverified
+
+    def _research(self, q: PreparedRows, y: PreparedRows, bad, k: int, exclude_self: bool,
+                  out_d, out_i):
+        """Rows `bad` (local query ids) whose proof failed: search them with the 3xTF32 kernel."""
+        self.search_stats["screen_unverified"] += int(bad.numel())
+        if bad.numel() == 0:
+            return
+        kk = k + 1 if exclude_self else k
+        d_b, i_b = self._search_tf32x3(q.take(bad), y, kk, exclude_self=False)
+        if exclude_self:
+            # the gathered queries lost their row numbers: drop the own id here (it is there
+            # unless duplicates of the row pushed it out, then drop the last)
+            own = bad + q.base
+            hit = i_b == own[:, None]
+            drop = torch.where(hit.any(dim=1), hit.to(torch.int8).argmax(dim=1),
+                               torch.full_like(own, kk - 1))
+            pos = torch.arange(k, device=bad.device)[None, :]
+            sel = pos + (pos >= drop[:, None]).to(pos.dtype)
+            d_b, i_b = d_b.gather(1, sel), i_b.gather(1, sel)
+        out_d[bad] = d_b
+        out_i[bad] = i_b
 
     # -- dual-direction pass ------------------------------------------------------
     FUSED_EMIT_TARGET = 384      # expected rows emitted per column (sets the sample size)
@@ -353,63 +455,93 @@ class B200Mixin:
         with torch.cuda.device(dev):
             st = lib.stream_ptr()
             sm = torch.cuda.get_device_properties(dev).multi_processor_count
+            screen = self._use_screen(rows, cols, cap, dual=True)
             # 1. column thresholds from a strided sample of the rows
             n_s = min(rows.n, max(8 * cap, -(-rows.n * cap // self.FUSED_EMIT_TARGET)))
             step = max(1, rows.n // n_s)
             sample = rows.take(torch.arange(n_s, device=dev, dtype=torch.int64) * step)
-            s_splits = lib.lib.kb2_suggest_splits(cols.n, n_s, cap, sm)
-            s_idx = torch.empty((cols.n, s_splits * cap), dtype=torch.int32, device=dev)
-            s_key = torch.empty((cols.n, s_splits * cap), dtype=torch.float32, device=dev)
             prof = getattr(self, "_profile", None)       # bench.py: CUDA events around the searches
-            if prof is not None:
-                ev0 = torch.cuda.Event(enable_timing=True)
-                ev0.record()
-            lib.call("kb2_knn_candidates", lib.KNN_AUTO, lib.ptr(cols.hi), lib.ptr(cols.lo), cols.n,
-                     lib.ptr(sample.hi), lib.ptr(sample.lo), lib.ptr(sample.key), n_s, rows.dpad,
-                     cap, s_splits, lib.ptr(s_idx), lib.ptr(s_key), st)
-            if prof is not None:
-                ev1 = torch.cuda.Event(enable_timing=True)
-                ev1.record()
-                prof.append((ev0, ev1, cols.n, n_s, rows.d))
+            if screen and self._use_screen(cols, sample, cap, dual=False):
+                _s_idx, s_key, lists = self._screen_search(cols, sample, cap)
+            else:
+                lists = lib.lib.kb2_suggest_splits(cols.n, n_s, cap, sm)
+                _s_idx = torch.empty((cols.n, lists * cap), dtype=torch.int32, device=dev)
+                s_key = torch.empty((cols.n, lists * cap), dtype=torch.float32, device=dev)
+                if prof is not None:
+                    ev0 = torch.cuda.Event(enable_timing=True)
+                    ev0.record()
+                lib.call("kb2_knn_candidates", lib.KNN_AUTO, lib.ptr(cols.hi), lib.ptr(cols.lo), cols.n,
+                         lib.ptr(sample.hi), lib.ptr(sample.lo), lib.ptr(sample.key), n_s, rows.dpad,
+                         cap, lists, lib.ptr(_s_idx), lib.ptr(s_key), st)
+                if prof is not None:
+                    ev1 = torch.cuda.Event(enable_timing=True)
+                    ev1.record()
+                    prof.append((ev0, ev1, cols.n, n_s, rows.d, "tf32x3"))
             # the cap-th best within ANY subset of the rows bounds the final cap-th best
-            tau = s_key.view(cols.n, s_splits, cap)[:, :, cap - 1].amin(dim=1).contiguous()
-            del s_idx, s_key
+            tau = s_key.view(cols.n, lists, cap)[:, :, cap - 1].amin(dim=1).contiguous()
+            del _s_idx, s_key
             # 2. the dual-direction pass
-            splits = lib.lib.kb2_suggest_splits(rows.n, cols.n, cap, sm)
             col_cap = self.FUSED_COL_CAP
             col_cnt = torch.zeros(cols.n, dtype=torch.int32, device=dev)
             col_buf = torch.empty((cols.n, col_cap), dtype=torch.int64, device=dev)
-            cand_rows = torch.empty((rows.n, splits * cap), dtype=torch.int32, device=dev)
-            if prof is not None:
-                ev0 = torch.cuda.Event(enable_timing=True)
-                ev0.record()
-            lib.call("kb2_knn_fused", lib.ptr(rows.hi), lib.ptr(rows.lo), lib.ptr(rows.key), rows.n,
-                     lib.ptr(cols.hi), lib.ptr(cols.lo), lib.ptr(cols.key), cols.n, rows.dpad, cap,
-                     splits, lib.ptr(tau), lib.ptr(col_cnt), lib.ptr(col_buf), col_cap,
-                     lib.ptr(cand_rows), st)
-            if prof is not None:
-                ev1 = torch.cuda.Event(enable_timing=True)
-                ev1.record()
-                prof.append((ev0, ev1, rows.n, cols.n, rows.d))
+            if screen:
+                cand_rows, key_rows, r_lists = self._screen_search(
+                    rows, cols, cap, dual=(tau, col_cnt, col_buf, col_cap))
+            else:
+                splits = lib.lib.kb2_suggest_splits(rows.n, cols.n, cap, sm)
+                cand_rows = torch.empty((rows.n, splits * cap), dtype=torch.int32, device=dev)
+                if prof is not None:
+                    ev0 = torch.cuda.Event(enable_timing=True)
+                    ev0.record()
+                lib.call("kb2_knn_fused", lib.ptr(rows.hi), lib.ptr(rows.lo), lib.ptr(rows.key), rows.n,
+                         lib.ptr(cols.hi), lib.ptr(cols.lo), lib.ptr(cols.key), cols.n, rows.dpad, cap,
+                         splits, lib.ptr(tau), lib.ptr(col_cnt), lib.ptr(col_buf), col_cap,
+                         lib.ptr(cand_rows), st)
+                if prof is not None:
+                    ev1 = torch.cuda.Event(enable_timing=True)
+                    ev1.record()
+                    prof.append((ev0, ev1, rows.n, cols.n, rows.d, "tf32x3-dual"))
             # 3. row side: exact finish of the row lists
-            fwd = self._refine(rows, cols, cand_rows, k_rows, exclude_self_rows)
+            if screen:
+                fwd_d, fwd_i, unv = self._refine_checked(
+                    rows, cols, cand_rows, k_rows, exclude_self_rows,
+                    lib.ptr(key_rows) + 4 * (cap - 1), r_lists * cap, cap, r_lists)
+                self.search_stats["screen_rows"] += rows.n
+                self._research(rows, cols, torch.nonzero(unv).flatten(), k_rows, exclude_self_rows,
+                               fwd_d, fwd_i)
+                fwd = (fwd_d, fwd_i)
+                del key_rows
+            else:
+                fwd = self._refine(rows, cols, cand_rows, k_rows, exclude_self_rows)
             # 4. column side: best cap emitted rows per column, exact finish
             cand_cols = torch.empty((cols.n, cap), dtype=torch.int32, device=dev)
             overflow = torch.empty(cols.n, dtype=torch.int32, device=dev)
+            col_tau = torch.empty(cols.n, dtype=torch.float32, device=dev) if screen else None
             lib.call("kb2_col_select", lib.ptr(col_buf), lib.ptr(col_cnt), cols.n, col_cap, cap,
-                     lib.ptr(cand_cols), lib.ptr(overflow), st)
+                     lib.ptr(cand_cols), lib.ptr(overflow), lib.ptr(tau) if screen else None,
+                     lib.ptr(col_tau), st)
             del col_buf
-            rev_d, rev_i = self._refine(cols, rows, cand_cols, k_cols, False)
-            bad = torch.nonzero(overflow).flatten()
+            if screen:
+                rev_d, rev_i, unv = self._refine_checked(cols, rows, cand_cols, k_cols, False,
+                                                         lib.ptr(col_tau), 1, 1, 1)
+                self.search_stats["screen_rows"] += cols.n
+                n_over = int(overflow.sum()) if prof is not None else 0
+                # overflowed columns lost rows below their threshold: search them again too
+                self._research(cols, rows, torch.nonzero(unv | overflow).flatten(), k_cols, False,
+                               rev_d, rev_i)
+            else:
+                rev_d, rev_i = self._refine(cols, rows, cand_cols, k_cols, False)
+                bad = torch.nonzero(overflow).flatten()
+                n_over = int(bad.numel())
+                if bad.numel():      # columns whose buffer overflowed: plain search for those few
+                    d_b, i_b = self._search_tf32x3(cols.take(bad), rows, k_cols)
+                    rev_d[bad] = d_b
+                    rev_i[bad] = i_b
             if prof is not None:
                 self._fused_stats = {"sample_rows": int(n_s), "col_cap": int(col_cap),
                                      "emitted_per_column_mean": float(col_cnt.float().mean()),
                                      "emitted_per_column_max": int(col_cnt.max()),
-                                     "overflow_columns": int(bad.numel())}
-            if bad.numel():      # columns whose buffer overflowed: plain search for those few
-                d_b, i_b = self.search(cols.take(bad), rows, k_cols)
-                rev_d[bad] = d_b
-                rev_i[bad] = i_b
+                                     "overflow_columns": n_over}
         return fwd, (rev_d, rev_i)
 
     def _refine(self, q: PreparedRows, y: PreparedRows, cand, k: int, exclude_self: bool):
@@ -435,6 +567,27 @@ class B200Mixin:
         lib = self._lib
         if q.d != y.d:
             raise ValueError(f"query has {q.d} features, index has {y.d}")
+        cap = min(candidate_capacity(k), lib.lib.kb2_max_candidates())
+        if k > cap:
+            raise ValueError(
+                f"B200 supports at most {lib.lib.kb2_max_candidates()} neighbours per "
+                f"query and shard, got {k}")
+        if q.n == 0 or splits is not None or not self._use_screen(q, y, cap, dual=False) \
+                or (exclude_self and y.n < k + 2):
+            return self._search_tf32x3(q, y, k, exclude_self=exclude_self, splits=splits)
+        with torch.cuda.device(self.device):
+            cand, ckey, lists = self._screen_search(q, y, cap)
+            out_d, out_i, unv = self._refine_checked(q, y, cand, k, exclude_self,
+                                                     lib.ptr(ckey) + 4 * (cap - 1), lists * cap, cap,
+                                                     lists)
+            self.search_stats["screen_rows"] += q.n
+            self._research(q, y, torch.nonzero(unv).flatten(), k, exclude_self, out_d, out_i)
+        return out_d, out_i
+
+    def _search_tf32x3(self, q: PreparedRows, y: PreparedRows, k: int, exclude_self: bool = False,
+                       splits: Optional[int] = None):
+        """The 3xTF32 search (knn_tc2.cu / knn_tc.cu / the SIMT cross-check) + exact finish."""
+        lib = self._lib
         dev = self.device
         with torch.cuda.device(dev):
             out_d = torch.empty((q.n, k), dtype=torch.float64, device=dev)
@@ -442,10 +595,6 @@ class B200Mixin:
             if q.n == 0:
                 return out_d, out_i
             cap = min(candidate_capacity(k), lib.lib.kb2_max_candidates())
-            if k > cap:
-                raise ValueError(
-                    f"B200 supports at most {lib.lib.kb2_max_candidates()} neighbours per "
-                    f"query and shard, got {k}")
             if splits is None:
                 sm = torch.cuda.get_device_properties(dev).multi_processor_count
                 splits = lib.lib.kb2_suggest_splits(q.n, y.n, cap, sm)
@@ -456,7 +605,6 @@ class B200Mixin:
             st = lib.stream_ptr()
             # self = index row j with j + self_offset == query row (ids local to q / y); the
             # search keeps it (one margin slot), the exact finish drops it by id
-            self_offset = y.base - q.base
             prof = getattr(self, "_profile", None)   # bench.py: CUDA events around the search
             if prof is not None:
                 ev0 = torch.cuda.Event(enable_timing=True)
@@ -467,7 +615,7 @@ class B200Mixin:
             if prof is not None:
                 ev1 = torch.cuda.Event(enable_timing=True)
                 ev1.record()
-                prof.append((ev0, ev1, q.n, y.n, q.d))
+                prof.append((ev0, ev1, q.n, y.n, q.d, "tf32x3"))
             out_d, out_i = self._refine(q, y, cand, k, exclude_self)
         return out_d, out_i
 
@@ -478,6 +626,10 @@ class B200(B200Mixin, NNAlgorithm):
     Parameters mirror SklearnNN where they apply (n_candidates, metric, p, n_jobs).
     ``impl``: "auto"/"tc" = tcgen05 tensor-core search (CTA pairs), "tc1" = its single-CTA
     form, "simt" = FP32-pipe cross-check.
+    ``precision``: "tf32x3" = every candidate key from the 3xTF32 split; "screen" / "auto" =
+    propose candidates with ONE TF32 product (3x fewer MMAs, knn_screen.cu), prove in the
+    float64 finish that the proposal contains the exact top k, search the few rows where the
+    proof fails again with 3xTF32 -- same results (``search_stats`` counts the fallbacks).
     ``distributed``: shard the index side over the ranks of an initialised
     torch.distributed (NCCL) group; default: on when world_size > 1.
     """

@@ -13,8 +13,14 @@ RTOL, ATOL = 1e-5, 5e-6   # north star: 1e-5 relative; atol covers sklearn's sqr
 
 
 def _algo(**kw):
+    """impl="screen" = the tcgen05 pair kernels with the 1xTF32 screen + proof + 3xTF32
+    re-search; every other impl pins the 3xTF32 keys so that both paths stay covered."""
     from kiez_b200 import B200
 
+    if kw.get("impl") == "screen":
+        kw.update(impl="tc", precision="screen")
+    else:
+        kw.setdefault("precision", "tf32x3")
     return B200(**kw)
 
 
@@ -49,7 +55,7 @@ SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("impl", ["tc", "tc1", "simt"])
+@pytest.mark.parametrize("impl", ["tc", "tc1", "simt", "screen"])
 @pytest.mark.parametrize(("nq", "ny", "d", "k"), SHAPES)
 @pytest.mark.parametrize("metric", ["euclidean", "cosine", "sqeuclidean"])
 def test_knn_matches_oracle(impl, nq, ny, d, k, metric):
@@ -68,7 +74,7 @@ def test_knn_matches_oracle(impl, nq, ny, d, k, metric):
                              what=f"rev {impl} {metric} {nq}x{ny}x{d}")
 
 
-@pytest.mark.parametrize("impl", ["tc", "tc1", "simt"])
+@pytest.mark.parametrize("impl", ["tc", "tc1", "simt", "screen"])
 @pytest.mark.parametrize("dist_kind", ["shifted", "hubby"])
 def test_knn_hard_distributions(impl, dist_kind):
     q, y = _data(700, 1500, 96, seed=3, dist=dist_kind)
@@ -80,7 +86,7 @@ def test_knn_hard_distributions(impl, dist_kind):
                              what=f"{impl} {dist_kind}")
 
 
-@pytest.mark.parametrize("impl", ["tc", "tc1", "simt"])
+@pytest.mark.parametrize("impl", ["tc", "tc1", "simt", "screen"])
 def test_self_query_excludes_self(impl):
     """sklearn kneighbors(X=None) semantics (neighbors/_base.py:937-958)."""
     q, _ = _data(600, 1, 40, seed=5)
@@ -147,14 +153,15 @@ def test_large_sampled_rows():
                                                    (2049, 4097, 256, 10), (5000, 700, 128, 50),
                                                    (700, 5000, 96, 24)])
 @pytest.mark.parametrize("single", [False, True])
-def test_fused_dual_direction_pass(nq, ny, d, c, single):
+@pytest.mark.parametrize("impl", ["tc", "screen"])
+def test_fused_dual_direction_pass(nq, ny, d, c, single, impl):
     """One contraction, both directions (B200.search_both): row-wise results must equal the
     forward search, column-wise results the reverse search, both equal to the oracle."""
     q, y = _data(nq, ny, d, seed=nq + d)
     if single:
         y = q
         ny = nq
-    algo = _algo(n_candidates=c, fused=True)
+    algo = _algo(n_candidates=c, fused=True, impl=impl)
     qp = algo._prepare(q, cache=False)
     yp = qp if single else algo._prepare(y, cache=False)
     k_fwd = min(c, ny - (1 if single else 0))
@@ -167,12 +174,107 @@ def test_fused_dual_direction_pass(nq, ny, d, c, single):
     O.assert_neighbors_match(rd.cpu().numpy(), ri.cpu().numpy(), want_d, want_i, RTOL, ATOL, what="rev")
 
 
-def test_fused_column_overflow_falls_back():
+@pytest.mark.parametrize("impl", ["tc", "screen"])
+def test_fused_column_overflow_falls_back(impl):
     """A column buffer that overflows (here: forced by a tiny capacity) is re-searched."""
     q, y = _data(3000, 400, 32, seed=8)
-    algo = _algo(n_candidates=10, fused=True)
+    algo = _algo(n_candidates=10, fused=True, impl=impl)
     algo.FUSED_COL_CAP = 16                  # == cap: every column with > 16 emitted rows overflows
     qp, yp = algo._prepare(q, cache=False), algo._prepare(y, cache=False)
     (_fd, _fi), (rd, ri) = algo.search_both(qp, yp, 10, 10)
     want_d, want_i = O.knn_brute(y.astype(np.float64), q.astype(np.float64), 10, "euclidean")
     O.assert_neighbors_match(rd.cpu().numpy(), ri.cpu().numpy(), want_d, want_i, RTOL, ATOL, what="rev")
+
+
+# ---------------------------------------------------------------------------
+# the 1xTF32 screen: proposals + float64 completeness proof + 3xTF32 re-search
+# ---------------------------------------------------------------------------
+def test_screen_is_used_and_mostly_proven():
+    q, y = _data(3000, 8000, 256, seed=21)
+    algo = _algo(n_candidates=10, impl="screen")
+    algo.fit(q, y)
+    dist, ind = algo.kneighbors(k=10)
+    st = dict(algo.search_stats)
+    assert st["screen_rows"] == 3000                       # the screen ran (no silent 3xTF32 path)
+    assert st["screen_unverified"] < 300                   # and its proof carried almost every row
+    want_d, want_i = O.knn_brute(q.astype(np.float64), y.astype(np.float64), 10, "euclidean")
+    O.assert_neighbors_match(dist.cpu().numpy(), ind.cpu().numpy(), want_d, want_i, RTOL, ATOL,
+                             what="screen")
+
+
+@pytest.mark.parametrize("single", [False, True])
+def test_screen_unproven_rows_are_searched_again(single):
+    """With an absurdly pessimistic error bound no row can be proven: every row must take the
+    3xTF32 re-search (self-exclusion included) and still equal the oracle."""
+    q, y = _data(900, 1200, 48, seed=22)
+    algo = _algo(n_candidates=8, impl="screen")
+    algo._eps_dot = lambda dpad: 5.0
+    if single:
+        algo.fit(q)
+        y = q
+    else:
+        algo.fit(q, y)
+    dist, ind = algo.kneighbors(k=8)
+    assert algo.search_stats["screen_unverified"] == algo.search_stats["screen_rows"] == 900
+    want_d, want_i = O.knn_brute(q.astype(np.float64), y.astype(np.float64), 8, "euclidean",
+                                 exclude_self=single)
+    O.assert_neighbors_match(dist.cpu().numpy(), ind.cpu().numpy(), want_d, want_i, RTOL, ATOL,
+                             what="re-search")
+
+
+@pytest.mark.parametrize("metric", ["euclidean", "cosine"])
+def test_screen_near_ties_need_the_proof(metric):
+    """Tight clusters: neighbours closer together than the TF32 rounding of the screen keys.
+    The proof must flag those rows (not silently accept a wrong list)."""
+    q, y = _data(1500, 4000, 64, seed=23, dist="hubby")
+    algo = _algo(n_candidates=10, metric=metric, impl="screen")
+    algo.fit(q, y)
+    dist, ind = algo.kneighbors(k=10)
+    assert algo.search_stats["screen_rows"] == 1500
+    want_d, want_i = O.knn_brute(q.astype(np.float64), y.astype(np.float64), 10, metric)
+    O.assert_neighbors_match(dist.cpu().numpy(), ind.cpu().numpy(), want_d, want_i, RTOL, ATOL,
+                             what=f"near ties {metric}")
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_screen_chained_ranges(monkeypatch, fused):
+    """Enough query tiles for the L2-blocked order: the index is cut into ranges that are
+    searched in order per query tile, the lists carried from range to range."""
+    monkeypatch.setenv("KB2_SCREEN_RANGE_MB", "0.25")      # 1024-row ranges at d = 64
+    nq, ny = 40000, 6100
+    q, y = _data(nq, ny, 64, seed=24)
+    algo = _algo(n_candidates=10, impl="screen", fused=fused)
+    qp, yp = algo._prepare(q, cache=False), algo._prepare(y, cache=False)
+    steps, chained = algo._screen_plan(nq, ny, 64, 16)
+    assert chained == 1 and steps == 6
+    rows = np.random.default_rng(1).choice(nq, 300, replace=False)
+    if fused:
+        (fd, fi), (rd, ri) = algo.search_both(qp, yp, 10, 10)
+        cols = np.random.default_rng(2).choice(ny, 200, replace=False)
+        want_d, want_i = O.knn_brute(y[cols].astype(np.float64), q.astype(np.float64), 10, "euclidean")
+        O.assert_neighbors_match(rd[cols].cpu().numpy(), ri[cols].cpu().numpy(), want_d, want_i,
+                                 RTOL, ATOL, what="chained rev")
+    else:
+        fd, fi = algo.search(qp, yp, 10)
+    want_d, want_i = O.knn_brute(q[rows].astype(np.float64), y.astype(np.float64), 10, "euclidean")
+    O.assert_neighbors_match(fd[rows].cpu().numpy(), fi[rows].cpu().numpy(), want_d, want_i,
+                             RTOL, ATOL, what="chained fwd")
+    assert algo.search_stats["screen_unverified"] < 0.05 * algo.search_stats["screen_rows"]
+
+
+def test_screen_not_taken_for_float64_or_wide_rows():
+    """float64 callers and d > 256 keep the 3xTF32 search (the proof assumes fp32 operands; the
+    resident query tile needs d <= 256)."""
+    rng = np.random.default_rng(3)
+    algo = _algo(n_candidates=5, impl="screen")
+    algo.fit(rng.standard_normal((200, 20)), rng.standard_normal((300, 20)))   # float64
+    algo.kneighbors(k=5)
+    assert algo.search_stats["screen_rows"] == 0
+    q, y = _data(200, 400, 300, seed=4)
+    algo = _algo(n_candidates=5, impl="screen")
+    algo.fit(q, y)
+    dist, ind = algo.kneighbors(k=5)
+    assert algo.search_stats["screen_rows"] == 0
+    want_d, want_i = O.knn_brute(q.astype(np.float64), y.astype(np.float64), 5, "euclidean")
+    O.assert_neighbors_match(dist.cpu().numpy(), ind.cpu().numpy(), want_d, want_i, RTOL, ATOL,
+                             what="wide rows")

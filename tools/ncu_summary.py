@@ -31,6 +31,32 @@ def ncu(path, page):
     return out
 
 
+def cuda_lines(path, tot_s, tot_i):
+    """Samples / instructions aggregated per CUDA source line (needs -lineinfo + --import-source)."""
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--print-source",
+                          "cuda,sass"], capture_output=True, text=True).stdout
+    fname, hdr, lines = "?", None, []
+    for r in csv.reader(io.StringIO(out)):
+        if not r:
+            continue
+        if r[0] == "File Path":
+            fname = r[1].split("/")[-1]
+        elif r[0] == "Line No":
+            hdr = r
+        elif hdr and r[0].isdigit() and len(r) == len(hdr):
+            d = dict(zip(hdr, r))
+            try:
+                lines.append((int(d["# Samples"]), int(d["Instructions Executed"]), fname, r[0],
+                              r[1].strip()))
+            except (KeyError, ValueError):
+                pass
+    if not lines:
+        return
+    print("# hottest CUDA source lines (samples %, executed warp instructions %)")
+    for smp, ins, f, ln, src in sorted(lines, reverse=True)[:30]:
+        print(f"  {100.0 * smp / tot_s:5.2f}% {100.0 * ins / tot_i:5.2f}%  {f}:{ln:>4s}  {src[:90]}")
+
+
 def main():
     path = sys.argv[1]
     raw = list(csv.reader(io.StringIO(ncu(path, "raw"))))
@@ -59,6 +85,7 @@ def main():
         top = max(stalls, key=lambda c: int(r[c]))
         print(f"  {100.0 * int(r['# Samples']) / tot_s:5.2f}% samples {100.0 * int(r['Instructions Executed']) / tot_i:5.2f}% inst  "
               f"{r['Source'][:64]:64s} {top}")
+    cuda_lines(path, tot_s, tot_i)
     mem = [r for r in rows if "LDL" in r["Source"] or "STL" in r["Source"]]
     print(f"# local-memory instructions in SASS: {len(mem)} "
           f"(executed {sum(int(r['Instructions Executed']) for r in mem)})")
