@@ -334,14 +334,19 @@ def run_b200(args, w):
               for k, v in groups.items()]
     detail.sort(key=lambda r: -r["nq"] * r["ny"])
     search_ms = sum(v["ms"] for v in groups.values())
-    if detail:
-        top = [r for r in detail if r["nq"] * r["ny"] == detail[0]["nq"] * detail[0]["ny"]
-               and r["kind"] == detail[0]["kind"]]
-        top_ms = sum(r["avg_launch_ms"] * r["launches"] for r in top)
-        top_n = sum(r["launches"] for r in top)
-        top_flop = 2.0 * top[0]["nq"] * top[0]["ny"] * top[0]["d"]
-        achieved = top_flop * top_n / (top_ms * 1e-3) / 1e12
-        kind = top[0]["kind"]
+    # the dominant kernel = the kind with the most algorithmic flops; its launches may differ in
+    # shape (row segments of the dual-direction pass): achieved = sum(flop) / sum(time)
+    by_kind = {}
+    for r in detail:
+        k = by_kind.setdefault(r["kind"], {"flop": 0.0, "ms": 0.0, "n": 0})
+        k["flop"] += 2.0 * r["nq"] * r["ny"] * r["d"] * r["launches"]
+        k["ms"] += r["avg_launch_ms"] * r["launches"]
+        k["n"] += r["launches"]
+    if by_kind:
+        kind = max(by_kind, key=lambda kk: by_kind[kk]["flop"])
+        top_ms, top_n = by_kind[kind]["ms"], by_kind[kind]["n"]
+        top_flop = by_kind[kind]["flop"] / top_n
+        achieved = by_kind[kind]["flop"] / (top_ms * 1e-3) / 1e12
     else:
         top_ms, top_n, top_flop, achieved, kind = 0.0, 0, 0.0, 0.0, "tf32x3"
     fused_stats = getattr(out_algo[0], "_fused_stats", None) if out_algo else None
@@ -366,7 +371,9 @@ def run_b200(args, w):
         "launches": top_n, "avg_launch_ms": (top_ms / top_n) if top_n else None,
         "kernel_share_of_step": (top_ms / ms) if ms else None,
         "all_search_launches_share_of_step": (search_ms / ms) if ms else None,
-        "algorithmic_flop_per_launch": top_flop, "search_launches": detail,
+        "algorithmic_flop_per_launch": top_flop,
+        "algorithmic_flop_per_step": (top_flop * top_n / args.steps) if top_n else None,
+        "search_launches": detail,
         "dual_direction": fused_stats, "screen": search_stats,
     }
     if rank == 0:

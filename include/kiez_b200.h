@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define KB2_VERSION 2
+#define KB2_VERSION 3
 
 /* metric codes (kiez SklearnNN metric names; minkowski/l2 are p=2 euclidean) */
 #define KB2_METRIC_EUCLIDEAN   0
@@ -98,11 +98,15 @@ int kb2_knn_candidates(int impl, const float *q_hi, const float *q_lo, int64_t n
  * must be searched separately).  tau_col must bound the column's final cap-th best key from
  * above, e.g. the cap-th best key against a sample of the rows.  Serves kiez's reverse pass
  * (hubness_reduction/base.py:37-42) and forward pass (:92-94) from ONE contraction.
+ * The rows may be passed in SEGMENTS (one call per contiguous row range, row_id_base = its
+ * first row: added to the emitted row ids) with kb2_col_compact between the calls, which
+ * tightens tau_col to the cap-th best key seen so far.
  */
 int kb2_knn_fused(const float *x_hi, const float *x_lo, const float *x_key, int64_t nx,
                   const float *y_hi, const float *y_lo, const float *y_key, int64_t ny,
                   int dpad, int cap, int splits, const float *tau_col, uint32_t *col_cnt,
-                  uint64_t *col_buf, int col_cap, int32_t *cand_idx, void *stream);
+                  uint64_t *col_buf, int col_cap, int64_t row_id_base, int32_t *cand_idx,
+                  void *stream);
 /* Per column: the cap emitted rows with the smallest column keys -> cand_idx [ny][cap]
  * (-1 padded), overflow[col] = 1 if more than col_cap rows were emitted.  Optional (both or
  * neither): tau_col = the thresholds the pass ran with, col_tau [ny] out = a lower bound of
@@ -110,6 +114,12 @@ int kb2_knn_fused(const float *x_hi, const float *x_lo, const float *x_key, int6
 int kb2_col_select(const uint64_t *col_buf, const uint32_t *col_cnt, int64_t ny, int col_cap,
                    int cap, int32_t *cand_idx, int32_t *overflow, const float *tau_col,
                    float *col_tau, void *stream);
+/* Between two row segments of a dual-direction pass: per column with >= cap emitted rows, the
+ * best cap entries move to the head of its buffer, col_cnt = cap and tau_col = the cap-th best
+ * key so far (thresholds only tighten, so the bound kb2_col_select reports stays valid).  A
+ * column with more than col_cap emitted rows keeps a sticky overflow count. */
+int kb2_col_compact(uint64_t *col_buf, uint32_t *col_cnt, int64_t ny, int col_cap, int cap,
+                    float *tau_col, void *stream);
 
 /*
  * Screening candidate search (knn_screen.cu): same contract as kb2_knn_candidates /
@@ -126,7 +136,8 @@ int kb2_col_select(const uint64_t *col_buf, const uint32_t *col_cnt, int64_t ny,
  *   cand_key is required (fp32 screen keys, ascending per list, +inf padded): the last key of
  *     a list is the tau of the proof.
  *   dual-direction form when tau_col != NULL: additionally appends to col_buf/col_cnt like
- *     kb2_knn_fused (q_key = the row-side selection terms).
+ *     kb2_knn_fused (q_key = the row-side selection terms, row_id_base = first row of the
+ *     segment).
  * kb2_screen_stages: pipeline stages the kernel gets for (dpad, cap); 0 = shape not
  *   supported (dpad > 256 or lists too long for the shared memory left by the query tile).
  */
@@ -136,7 +147,8 @@ int kb2_screen_plan(int64_t nq, int64_t ny, int dpad, int cap, int sm_count, int
 int kb2_knn_screen(const float *q_hi, const float *q_key, int64_t nq, const float *y_hi,
                    const float *y_key, int64_t ny, int dpad, int cap, int steps, int chained,
                    int32_t *cand_idx, float *cand_key, int32_t *chain_flag, const float *tau_col,
-                   uint32_t *col_cnt, uint64_t *col_buf, int col_cap, void *stream);
+                   uint32_t *col_cnt, uint64_t *col_buf, int col_cap, int64_t row_id_base,
+                   void *stream);
 /* max(0, max_i x[i]) -> *out (device): the largest selection term ||y - center||^2 of an
  * index, input of the completeness proof. */
 int kb2_max_f32(const float *x, int64_t n, float *out, void *stream);

@@ -31,12 +31,14 @@ SIGNATURES = {
     "kb2_suggest_splits": [_i64, _i64, _int, _int],
     "kb2_prepare_rows": [_p, _i64, _int, _i64, _p, _int, _p, _p, _int, _p, _p, _p],
     "kb2_knn_candidates": [_int, _p, _p, _i64, _p, _p, _p, _i64, _int, _int, _int, _p, _p, _p],
-    "kb2_knn_fused": [_p, _p, _p, _i64, _p, _p, _p, _i64, _int, _int, _int, _p, _p, _p, _int, _p, _p],
+    "kb2_knn_fused": [_p, _p, _p, _i64, _p, _p, _p, _i64, _int, _int, _int, _p, _p, _p, _int, _i64,
+                      _p, _p],
     "kb2_col_select": [_p, _p, _i64, _int, _int, _p, _p, _p, _p, _p],
+    "kb2_col_compact": [_p, _p, _i64, _int, _int, _p, _p],
     "kb2_screen_stages": [_int, _int, _int],
     "kb2_screen_plan": [_i64, _i64, _int, _int, _int, _p, _p],
     "kb2_knn_screen": [_p, _p, _i64, _p, _p, _i64, _int, _int, _int, _int, _p, _p, _p, _p, _p, _p,
-                       _int, _p],
+                       _int, _i64, _p],
     "kb2_max_f32": [_p, _i64, _p, _p],
     "kb2_refine_topk_checked": [_p, _i64, _i64, _p, _i64, _i64, _int, _int, _p, _p, _p, _int, _int,
                                 _i64, _int, _i64, _int, _p, _p, _p, _i64, _int, _int, _p, _p, _dbl,

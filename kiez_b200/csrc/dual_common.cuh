@@ -15,21 +15,44 @@ struct FusedParams {
     unsigned int *col_cnt;       // [ny] rows emitted so far (may exceed col_cap: overflow)
     ent_t *col_buf;              // [ny][col_cap] packed (column key, row)
     int col_cap;
+    int row_id_base;             // added to the emitted row ids (the pass covers a row segment)
 };
 
-// The emit queue of one column-epilogue warp (shared memory).
+// The emit queue of one column-epilogue warp (shared memory) + the previous drain, whose slot
+// claims (atomicAdd results) are still in flight: they are consumed by the NEXT drain, so a warp
+// never waits one L2 round trip (~1.5 k cycles) per drain.  That wait used to land in the tile
+// time of all 16 epilogue warps of the pair through tmem_empty.
 struct EmitQueue {
     float *key;
     int *col;
     unsigned char *lane;
     int n;                       // pending emits (warp-uniform)
+    ent_t pend_ent;              // this lane's entry of the previous drain: packed (column key, row)
+    int pend_col;                // its column, -1 = none
+    unsigned int pend_pos;       // its slot: result of the atomicAdd issued by the previous drain
 };
 
+__device__ __forceinline__ void emit_queue_init(EmitQueue &Q) {
+    Q.n = 0;
+    Q.pend_ent = 0;
+    Q.pend_col = -1;
+    Q.pend_pos = 0;
+}
+
+// Write the entries whose slots the previous drain claimed.
+__device__ __forceinline__ void emit_retire(const FusedParams &FP, EmitQueue &Q) {
+    if (Q.pend_col >= 0 && Q.pend_pos < (unsigned int)FP.col_cap)
+        FP.col_buf[(size_t)Q.pend_col * FP.col_cap + Q.pend_pos] = Q.pend_ent;
+    Q.pend_col = -1;
+}
+
 // Drain up to 32 pending emits of a warp: lane i claims a slot of its entry's column buffer
-// (32 independent atomics in flight) and writes (column key, row); the rest moves down.
+// (32 independent atomics in flight) and keeps (column key, row) for emit_retire; the rest of
+// the queue moves down.
 __device__ __forceinline__ void emit_flush(const FusedParams &FP, EmitQueue &Q, int64_t row_base,
                                            int lane) {
     __syncwarp();
+    emit_retire(FP, Q);
     const int take = min(Q.n, 32);
     float key = 0.f;
     int col = 0, owner = 0;
@@ -39,9 +62,9 @@ __device__ __forceinline__ void emit_flush(const FusedParams &FP, EmitQueue &Q, 
     const bool more = lane + 32 < Q.n;
     if (more) { key2 = Q.key[lane + 32]; col2 = Q.col[lane + 32]; owner2 = Q.lane[lane + 32]; }
     if (lane < take) {
-        const unsigned int pos = atomicAdd(FP.col_cnt + col, 1u);
-        if (pos < (unsigned int)FP.col_cap)
-            FP.col_buf[(size_t)col * FP.col_cap + pos] = pack_entry(key, (int)(row_base + owner));
+        Q.pend_pos = atomicAdd(FP.col_cnt + col, 1u);
+        Q.pend_ent = pack_entry(key, (int)(row_base + owner) + FP.row_id_base);
+        Q.pend_col = col;
     }
     __syncwarp();
     if (more) { Q.key[lane] = key2; Q.col[lane] = col2; Q.lane[lane] = (unsigned char)owner2; }

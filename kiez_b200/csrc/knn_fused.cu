@@ -229,7 +229,7 @@ knn_fused_kernel(const __grid_constant__ CUtensorMap map_q_hi,
         Q.key = emit_key + quad * EMIT_Q;
         Q.col = emit_col + quad * EMIT_Q;
         Q.lane = emit_lane + quad * EMIT_Q;
-        Q.n = 0;
+        emit_queue_init(Q);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int64_t u = pair_id; u < num_units; u += num_pairs) {
@@ -260,6 +260,7 @@ knn_fused_kernel(const __grid_constant__ CUtensorMap map_q_hi,
             }
             while (Q.n > 0) emit_flush(FP, Q, row_base, lane);   // rows change with the unit
         }
+        emit_retire(FP, Q);                                      // the last drain's entries
     }
 
     tc_fence_before();
@@ -272,24 +273,9 @@ knn_fused_kernel(const __grid_constant__ CUtensorMap map_q_hi,
     }
 }
 
-// Per column: keep the `cap` emitted rows with the smallest column keys (ties: lower row).
-// One warp per column, bitonic sort of the packed entries in shared memory.
-constexpr int CS_WARPS = 4;
-__global__ void __launch_bounds__(CS_WARPS * 32)
-col_select_kernel(const ent_t *__restrict__ col_buf, const unsigned int *__restrict__ col_cnt,
-                  int64_t ny, int col_cap, int P2, int cap, int32_t *__restrict__ cand_idx,
-                  int32_t *__restrict__ overflow, const float *__restrict__ tau_col,
-                  float *__restrict__ col_tau) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    ent_t *e = reinterpret_cast<ent_t *>(smem_raw) + (size_t)warp * P2;
-    const int64_t col = (int64_t)blockIdx.x * CS_WARPS + warp;
-    if (col >= ny) return;
-    const unsigned int total = col_cnt[col];
-    const int n = (int)min(total, (unsigned int)col_cap);
-    if (lane == 0) overflow[col] = total > (unsigned int)col_cap;
-    for (int i = lane; i < P2; i += 32) e[i] = (i < n) ? col_buf[(size_t)col * col_cap + i] : EMPTY_ENTRY;
-    // sort only as much as needed: the smallest power of two holding the n entries
+// Sort the first n entries of a column (in the warp's shared-memory slice e[0..P2), padded with
+// EMPTY_ENTRY) ascending: bitonic network over the smallest power of two holding them.
+__device__ __forceinline__ void col_sort(ent_t *e, int n, int lane) {
     int Pn = 32;
     while (Pn < n) Pn <<= 1;
     for (int size = 2; size <= Pn; size <<= 1) {
@@ -305,10 +291,54 @@ col_select_kernel(const ent_t *__restrict__ col_buf, const unsigned int *__restr
         }
     }
     __syncwarp();
-    for (int p = lane; p < cap; p += 32) cand_idx[col * cap + p] = (p < n) ? entry_col(e[p]) : -1;
-    // every row that was not kept has column key >= col_tau: emitted rows beyond the cap-th
-    // best by the sort, rows never emitted by the threshold test
-    if (col_tau && lane == 0) col_tau[col] = (n >= cap) ? entry_key(e[cap - 1]) : tau_col[col];
+}
+
+constexpr unsigned int COL_OVERFLOWED = 0x40000000u;   // sticky col_cnt value of a lost column
+
+// Per column: keep the `cap` emitted rows with the smallest column keys (ties: lower row).
+// One warp per column, bitonic sort of the packed entries in shared memory.
+//   COMPACT = false (after the last row segment): cand_idx / overflow / col_tau out.
+//   COMPACT = true (between row segments): the best cap entries go back to the head of the
+//     column's buffer, col_cnt = cap, and tau_col tightens to the cap-th best key so far -- the
+//     next segment emits ~cap * (its rows / rows seen so far) rows per column instead of
+//     ~cap * (its rows / sample rows).  A column that overflowed keeps a sticky count.
+constexpr int CS_WARPS = 4;
+template <bool COMPACT>
+__global__ void __launch_bounds__(CS_WARPS * 32)
+col_select_kernel(ent_t *__restrict__ col_buf, unsigned int *__restrict__ col_cnt,
+                  int64_t ny, int col_cap, int P2, int cap, int32_t *__restrict__ cand_idx,
+                  int32_t *__restrict__ overflow, float *__restrict__ tau_col,
+                  float *__restrict__ col_tau) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    ent_t *e = reinterpret_cast<ent_t *>(smem_raw) + (size_t)warp * P2;
+    const int64_t col = (int64_t)blockIdx.x * CS_WARPS + warp;
+    if (col >= ny) return;
+    const unsigned int total = col_cnt[col];
+    const int n = (int)min(total, (unsigned int)col_cap);
+    if constexpr (COMPACT) {
+        if (total > (unsigned int)col_cap) {
+            if (lane == 0) col_cnt[col] = COL_OVERFLOWED;
+            return;
+        }
+        if (n < cap) return;                               // everything is kept, tau_col stands
+    } else {
+        if (lane == 0) overflow[col] = total > (unsigned int)col_cap;
+    }
+    for (int i = lane; i < P2; i += 32) e[i] = (i < n) ? col_buf[(size_t)col * col_cap + i] : EMPTY_ENTRY;
+    col_sort(e, n, lane);
+    if constexpr (COMPACT) {
+        for (int p = lane; p < cap; p += 32) col_buf[(size_t)col * col_cap + p] = e[p];
+        if (lane == 0) {
+            col_cnt[col] = (unsigned int)cap;
+            tau_col[col] = entry_key(e[cap - 1]);
+        }
+    } else {
+        for (int p = lane; p < cap; p += 32) cand_idx[col * cap + p] = (p < n) ? entry_col(e[p]) : -1;
+        // every row that was not kept has column key >= col_tau: emitted rows beyond the cap-th
+        // best by the sort, rows never emitted by the threshold test (thresholds only tighten)
+        if (col_tau && lane == 0) col_tau[col] = (n >= cap) ? entry_key(e[cap - 1]) : tau_col[col];
+    }
 }
 
 static size_t fused_stage_bytes(int bk) { return (size_t)(2 * BM + 2 * F_HALF) * bk * 4; }
@@ -346,14 +376,15 @@ using namespace kb2;
 extern "C" int kb2_knn_fused(const float *x_hi, const float *x_lo, const float *x_key, int64_t nx,
                              const float *y_hi, const float *y_lo, const float *y_key, int64_t ny,
                              int dpad, int cap, int splits, const float *tau_col,
-                             uint32_t *col_cnt, uint64_t *col_buf, int col_cap, int32_t *cand_idx,
-                             void *stream) {
+                             uint32_t *col_cnt, uint64_t *col_buf, int col_cap, int64_t row_id_base,
+                             int32_t *cand_idx, void *stream) {
     KB2_CHECK(nx > 0 && ny > 0, "knn_fused: bad shape nx=%lld ny=%lld", (long long)nx, (long long)ny);
     KB2_CHECK(nx < (1LL << 31) - 256 && ny < (1LL << 31) - 256, "knn_fused: more than 2^31 rows");
     KB2_CHECK(dpad > 0 && dpad % 32 == 0, "knn_fused: dpad=%d must be a multiple of 32", dpad);
     KB2_CHECK(cap > 0 && cap <= 64, "knn_fused: cap=%d outside (0, 64]", cap);
     KB2_CHECK(splits >= 1 && (int64_t)splits * cap <= 2048, "knn_fused: splits*cap exceeds 2048");
     KB2_CHECK(col_cap >= cap && col_cap <= 4096, "knn_fused: col_cap=%d outside [cap, 4096]", col_cap);
+    KB2_CHECK(row_id_base >= 0 && row_id_base + nx < (1LL << 31), "knn_fused: row ids exceed 2^31");
     int dev = 0, sm_count = 0, max_smem = 0;
     KB2_CUDA(cudaGetDevice(&dev));
     KB2_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
@@ -366,6 +397,7 @@ extern "C" int kb2_knn_fused(const float *x_hi, const float *x_lo, const float *
     FusedParams FP;
     FP.x_key = x_key; FP.tau_col = tau_col; FP.col_cnt = col_cnt;
     FP.col_buf = reinterpret_cast<ent_t *>(col_buf); FP.col_cap = col_cap;
+    FP.row_id_base = (int)row_id_base;
     auto stages_for = [&](int bk, int slots) {
         const size_t fixed = tc_fixed_smem(F_BN, cap, slots, 8) + EMIT_WORDS * sizeof(float);
         if (fixed >= (size_t)max_smem) return 0;
@@ -382,19 +414,45 @@ extern "C" int kb2_knn_fused(const float *x_hi, const float *x_lo, const float *
     return launch_fused_cfg<16>(P, FP, x_hi, x_lo, y_hi, y_lo, dpad, stages, sm_count, max_smem, st);
 }
 
+static int col_select_launch(bool compact, uint64_t *col_buf, uint32_t *col_cnt, int64_t ny,
+                             int col_cap, int cap, int32_t *cand_idx, int32_t *overflow,
+                             float *tau_col, float *col_tau, cudaStream_t stream) {
+    const int P2 = max(32, next_pow2(col_cap));   // the sort network starts at 32 entries
+    const size_t smem = (size_t)CS_WARPS * P2 * sizeof(ent_t);
+    const unsigned grid = (unsigned)ceil_div64(ny, CS_WARPS);
+    ent_t *buf = reinterpret_cast<ent_t *>(col_buf);
+    if (compact) {
+        KB2_CUDA(cudaFuncSetAttribute(col_select_kernel<true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        col_select_kernel<true><<<grid, CS_WARPS * 32, smem, stream>>>(
+            buf, col_cnt, ny, col_cap, P2, cap, cand_idx, overflow, tau_col, col_tau);
+    } else {
+        KB2_CUDA(cudaFuncSetAttribute(col_select_kernel<false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        col_select_kernel<false><<<grid, CS_WARPS * 32, smem, stream>>>(
+            buf, col_cnt, ny, col_cap, P2, cap, cand_idx, overflow, tau_col, col_tau);
+    }
+    KB2_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" int kb2_col_select(const uint64_t *col_buf, const uint32_t *col_cnt, int64_t ny,
                               int col_cap, int cap, int32_t *cand_idx, int32_t *overflow,
                               const float *tau_col, float *col_tau, void *stream) {
     KB2_CHECK(ny >= 0 && cap > 0 && col_cap >= cap && col_cap <= 4096, "col_select: bad arguments");
+    KB2_CHECK(cand_idx && overflow, "col_select: cand_idx and overflow are required");
     KB2_CHECK(!col_tau || tau_col, "col_select: col_tau needs the tau_col the pass ran with");
     if (ny == 0) return 0;
-    const int P2 = max(32, next_pow2(col_cap));   // the sort network starts at 32 entries
-    const size_t smem = (size_t)CS_WARPS * P2 * sizeof(ent_t);
-    KB2_CUDA(cudaFuncSetAttribute(col_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
-    col_select_kernel<<<(unsigned)ceil_div64(ny, CS_WARPS), CS_WARPS * 32, smem,
-                        (cudaStream_t)stream>>>(reinterpret_cast<const ent_t *>(col_buf), col_cnt, ny,
-                                                col_cap, P2, cap, cand_idx, overflow, tau_col, col_tau);
-    KB2_LAUNCH_CHECK();
-    return 0;
+    return col_select_launch(false, const_cast<uint64_t *>(col_buf), const_cast<uint32_t *>(col_cnt),
+                             ny, col_cap, cap, cand_idx, overflow, const_cast<float *>(tau_col),
+                             col_tau, (cudaStream_t)stream);
+}
+
+extern "C" int kb2_col_compact(uint64_t *col_buf, uint32_t *col_cnt, int64_t ny, int col_cap,
+                               int cap, float *tau_col, void *stream) {
+    KB2_CHECK(ny >= 0 && cap > 0 && col_cap >= cap && col_cap <= 4096, "col_compact: bad arguments");
+    KB2_CHECK(col_buf && col_cnt && tau_col, "col_compact: NULL argument");
+    if (ny == 0) return 0;
+    return col_select_launch(true, col_buf, col_cnt, ny, col_cap, cap, nullptr, nullptr, tau_col,
+                             nullptr, (cudaStream_t)stream);
 }

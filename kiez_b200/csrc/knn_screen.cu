@@ -311,7 +311,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap map_q,
         Q.key = emit_key + quad * EMIT_Q;
         Q.col = emit_col + quad * EMIT_Q;
         Q.lane = emit_lane + quad * EMIT_Q;
-        Q.n = 0;
+        emit_queue_init(Q);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int64_t u = pair_id; u < num_units; u += num_pairs) {
@@ -342,6 +342,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap map_q,
             }
             while (Q.n > 0) emit_flush(FP, Q, row_base, lane);   // rows change with the unit
         }
+        emit_retire(FP, Q);                                      // the last drain's entries
     }
 
     // no CTA may exit (or free TMEM) while its peer can still signal its barriers
@@ -439,7 +440,7 @@ extern "C" int kb2_knn_screen(const float *q_hi, const float *q_key, int64_t nq,
                               const float *y_key, int64_t ny, int dpad, int cap, int steps,
                               int chained, int32_t *cand_idx, float *cand_key, int32_t *chain_flag,
                               const float *tau_col, uint32_t *col_cnt, uint64_t *col_buf,
-                              int col_cap, void *stream) {
+                              int col_cap, int64_t row_id_base, void *stream) {
     KB2_CHECK(nq > 0 && ny > 0, "knn_screen: bad shape nq=%lld ny=%lld", (long long)nq, (long long)ny);
     KB2_CHECK(nq < (1LL << 31) - 256 && ny < (1LL << 31) - 256, "knn_screen: more than 2^31 rows");
     KB2_CHECK(steps >= 1 && (chained || (int64_t)steps * cap <= 2048),
@@ -449,6 +450,7 @@ extern "C" int kb2_knn_screen(const float *q_hi, const float *q_key, int64_t nq,
     const bool dual = tau_col != nullptr;
     KB2_CHECK(!dual || (q_key && col_cnt && col_buf && col_cap >= cap && col_cap <= 4096),
               "knn_screen: the dual-direction form needs q_key, col_cnt, col_buf and col_cap in [cap, 4096]");
+    KB2_CHECK(row_id_base >= 0 && row_id_base + nq < (1LL << 31), "knn_screen: row ids exceed 2^31");
     int dev = 0, sm_count = 0, max_smem = 0;
     KB2_CUDA(cudaGetDevice(&dev));
     KB2_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
@@ -470,6 +472,7 @@ extern "C" int kb2_knn_screen(const float *q_hi, const float *q_key, int64_t nq,
     FusedParams FP;
     FP.x_key = q_key; FP.tau_col = tau_col; FP.col_cnt = col_cnt;
     FP.col_buf = reinterpret_cast<ent_t *>(col_buf); FP.col_cap = col_cap;
+    FP.row_id_base = (int)row_id_base;
     cudaStream_t st = (cudaStream_t)stream;
     if (dual) return launch_screen<true>(P, FP, q_hi, y_hi, dpad, sm_count, max_smem, st);
     return launch_screen<false>(P, FP, q_hi, y_hi, dpad, sm_count, max_smem, st);

@@ -15,6 +15,7 @@ graft it onto the *real* ``kiez.neighbors.NNAlgorithm`` when kiez is installed.
 """
 from __future__ import annotations
 
+import os
 import warnings
 from abc import ABC, abstractmethod
 from typing import Any, Optional, Tuple
@@ -374,13 +375,13 @@ class B200Mixin:
         if dual is None:
             lib.call("kb2_knn_screen", lib.ptr(q.hi), None, q.n, lib.ptr(y.hi), lib.ptr(y.key), y.n,
                      q.dpad, cap, steps, chained, lib.ptr(cand), lib.ptr(ckey), lib.ptr(flag),
-                     None, None, None, 0, lib.stream_ptr())
+                     None, None, None, 0, 0, lib.stream_ptr())
         else:
-            tau, col_cnt, col_buf, col_cap = dual
+            tau, col_cnt, col_buf, col_cap, row_id_base = dual
             lib.call("kb2_knn_screen", lib.ptr(q.hi), lib.ptr(q.key), q.n, lib.ptr(y.hi),
                      lib.ptr(y.key), y.n, q.dpad, cap, steps, chained, lib.ptr(cand), lib.ptr(ckey),
                      lib.ptr(flag), lib.ptr(tau), lib.ptr(col_cnt), lib.ptr(col_buf), col_cap,
-                     lib.stream_ptr())
+                     row_id_base, lib.stream_ptr())
         if prof is not None:
             ev1 = torch.cuda.Event(enable_timing=True)
             ev1.record()
@@ -388,13 +389,17 @@ class B200Mixin:
         return cand, ckey, lists
 
     def _refine_checked(self, q: PreparedRows, y: PreparedRows, cand, k: int, exclude_self: bool,
-                        tau, tau_row_stride: int, tau_step: int, tau_count: int):
-        """Exact finish + completeness proof; returns (dist, ind, unverified int32 [nq])."""
+                        tau, tau_row_stride: int, tau_step: int, tau_count: int, out=None):
+        """Exact finish + completeness proof; returns (dist, ind, unverified int32 [nq]), written
+        into the contiguous `out` triple when given."""
         lib = self._lib
         dev = self.device
-        out_d = torch.empty((q.n, k), dtype=torch.float64, device=dev)
-        out_i = torch.empty((q.n, k), dtype=torch.int64, device=dev)
-        unverified = torch.empty((q.n,), dtype=torch.int32, device=dev)
+        if out is not None:
+            out_d, out_i, unverified = out
+        else:
+            out_d = torch.empty((q.n, k), dtype=torch.float64, device=dev)
+            out_i = torch.empty((q.n, k), dtype=torch.int64, device=dev)
+            unverified = torch.empty((q.n,), dtype=torch.int32, device=dev)
         lib.call("kb2_refine_topk_checked", lib.ptr(q.raw), q.n, q.raw.stride(0), lib.ptr(y.raw), y.n,
                  y.raw.stride(0), q.d, 4, lib.ptr(q.sqnorm), lib.ptr(y.sqnorm), lib.ptr(cand),
                  cand.shape[1], self._metric_code, y.base, int(exclude_self), y.base - q.base, k,
@@ -425,8 +430,16 @@ class B200Mixin:
         out_i[bad] = i_b
 
     # -- dual-direction pass ------------------------------------------------------
-    FUSED_EMIT_TARGET = 384      # expected rows emitted per column (sets the sample size)
-    FUSED_COL_CAP = 1024         # slots per column buffer
+    # The column thresholds start from a search of the columns against a strided SAMPLE of the
+    # rows (rows / FUSED_SAMPLE_DIV of them) and tighten between row SEGMENTS whose sizes grow
+    # geometrically (each segment ~ (FUSED_SEGMENT_GROWTH - 1) x the rows seen before it), so a
+    # column receives ~cap (growth - 1) emits per segment: ~cap log2(DIV) in total at growth 2
+    # instead of cap * DIV from one threshold.  Measured at C4 the pass costs ~1.2 ms per emitted
+    # row per column (profiles/r01_ab_experiments.md block H).  KB2_FUSED_* override for tuning.
+    FUSED_SAMPLE_DIV = float(os.environ.get("KB2_FUSED_SAMPLE_DIV", "32"))
+    FUSED_SEGMENT_GROWTH = float(os.environ.get("KB2_FUSED_GROWTH", "2"))     # <= 1: one segment
+    FUSED_SEGMENT_MIN_ROWS = int(os.environ.get("KB2_FUSED_MIN_ROWS", "16384"))
+    FUSED_COL_CAP = int(os.environ.get("KB2_FUSED_COL_CAP", "512"))          # slots per column buffer
 
     def _use_fused(self, rows: PreparedRows, cols: PreparedRows, k: int) -> bool:
         if self.fused is False or self.impl in ("simt", "tc1"):
@@ -443,7 +456,28 @@ class B200Mixin:
             return False
         world = torch.distributed.get_world_size() if self.distributed else 1
         free, _total = torch.cuda.mem_get_info(self.device)
-        return (cols.n // world + 1) * self.FUSED_COL_CAP * 8 < 0.4 * free
+        return (cols.n // world + 1) * self._fused_col_cap(cap) * 8 < 0.4 * free
+
+    def _fused_col_cap(self, cap: int) -> int:
+        return max(self.FUSED_COL_CAP, cap)
+
+    def _fused_sample_rows(self, n_rows: int, cap: int) -> int:
+        return int(min(n_rows, max(8 * cap, -(-n_rows // max(1.0, self.FUSED_SAMPLE_DIV)))))
+
+    def _fused_segments(self, n_rows: int, n_sample: int):
+        """Row segment boundaries [0, b1, ..., n_rows] (multiples of 256 = one tile pair)."""
+        g = self.FUSED_SEGMENT_GROWTH
+        if g <= 1.0:
+            return [0, n_rows]
+        bounds, seen = [0], max(1, n_sample)
+        while bounds[-1] < n_rows:
+            size = max(int((g - 1.0) * seen), self.FUSED_SEGMENT_MIN_ROWS, 256)
+            nxt = (bounds[-1] + size + 255) // 256 * 256
+            if n_rows - nxt < size // 2:        # fold a short tail into this segment
+                nxt = n_rows
+            bounds.append(min(n_rows, nxt))
+            seen += bounds[-1] - bounds[-2]
+        return bounds
 
     def search_both(self, rows: PreparedRows, cols: PreparedRows, k_rows: int, k_cols: int,
                     exclude_self_rows: bool = False):
@@ -456,11 +490,11 @@ class B200Mixin:
             st = lib.stream_ptr()
             sm = torch.cuda.get_device_properties(dev).multi_processor_count
             screen = self._use_screen(rows, cols, cap, dual=True)
+            prof = getattr(self, "_profile", None)       # bench.py: CUDA events around the searches
             # 1. column thresholds from a strided sample of the rows
-            n_s = min(rows.n, max(8 * cap, -(-rows.n * cap // self.FUSED_EMIT_TARGET)))
+            n_s = self._fused_sample_rows(rows.n, cap)
             step = max(1, rows.n // n_s)
             sample = rows.take(torch.arange(n_s, device=dev, dtype=torch.int64) * step)
-            prof = getattr(self, "_profile", None)       # bench.py: CUDA events around the searches
             if screen and self._use_screen(cols, sample, cap, dual=False):
                 _s_idx, s_key, lists = self._screen_search(cols, sample, cap)
             else:
@@ -479,41 +513,56 @@ class B200Mixin:
                     prof.append((ev0, ev1, cols.n, n_s, rows.d, "tf32x3"))
             # the cap-th best within ANY subset of the rows bounds the final cap-th best
             tau = s_key.view(cols.n, lists, cap)[:, :, cap - 1].amin(dim=1).contiguous()
-            del _s_idx, s_key
-            # 2. the dual-direction pass
-            col_cap = self.FUSED_COL_CAP
+            del _s_idx, s_key, sample
+            # 2. the dual-direction pass, one launch per row segment; exact finish of the row
+            #    lists per segment; thresholds tighten between segments
+            col_cap = self._fused_col_cap(cap)
             col_cnt = torch.zeros(cols.n, dtype=torch.int32, device=dev)
             col_buf = torch.empty((cols.n, col_cap), dtype=torch.int64, device=dev)
+            fwd_d = torch.empty((rows.n, k_rows), dtype=torch.float64, device=dev)
+            fwd_i = torch.empty((rows.n, k_rows), dtype=torch.int64, device=dev)
+            unv_rows = torch.empty((rows.n,), dtype=torch.int32, device=dev) if screen else None
+            bounds = self._fused_segments(rows.n, n_s)
+            emitted = torch.zeros((), dtype=torch.int64, device=dev) if prof is not None else None
+            for lo, hi in zip(bounds[:-1], bounds[1:]):
+                seg = rows.rows(lo, hi)
+                if screen:
+                    cand_rows, key_rows, r_lists = self._screen_search(
+                        seg, cols, cap, dual=(tau, col_cnt, col_buf, col_cap, lo))
+                    self._refine_checked(seg, cols, cand_rows, k_rows, exclude_self_rows,
+                                         lib.ptr(key_rows) + 4 * (cap - 1), r_lists * cap, cap, r_lists,
+                                         out=(fwd_d[lo:hi], fwd_i[lo:hi], unv_rows[lo:hi]))
+                    del key_rows
+                else:
+                    splits = lib.lib.kb2_suggest_splits(seg.n, cols.n, cap, sm)
+                    cand_rows = torch.empty((seg.n, splits * cap), dtype=torch.int32, device=dev)
+                    if prof is not None:
+                        ev0 = torch.cuda.Event(enable_timing=True)
+                        ev0.record()
+                    lib.call("kb2_knn_fused", lib.ptr(seg.hi), lib.ptr(seg.lo), lib.ptr(seg.key), seg.n,
+                             lib.ptr(cols.hi), lib.ptr(cols.lo), lib.ptr(cols.key), cols.n, rows.dpad,
+                             cap, splits, lib.ptr(tau), lib.ptr(col_cnt), lib.ptr(col_buf), col_cap,
+                             lo, lib.ptr(cand_rows), st)
+                    if prof is not None:
+                        ev1 = torch.cuda.Event(enable_timing=True)
+                        ev1.record()
+                        prof.append((ev0, ev1, seg.n, cols.n, rows.d, "tf32x3-dual"))
+                    self._refine(seg, cols, cand_rows, k_rows, exclude_self_rows,
+                                 out=(fwd_d[lo:hi], fwd_i[lo:hi]))
+                del cand_rows
+                if hi < rows.n:
+                    if emitted is not None:     # sticky overflow counts are not emits
+                        emitted += torch.where(col_cnt < (1 << 30), col_cnt, 0).sum()
+                    lib.call("kb2_col_compact", lib.ptr(col_buf), lib.ptr(col_cnt), cols.n, col_cap,
+                             cap, lib.ptr(tau), st)
+                    if emitted is not None:
+                        emitted -= torch.where(col_cnt < (1 << 30), col_cnt, 0).sum()
             if screen:
-                cand_rows, key_rows, r_lists = self._screen_search(
-                    rows, cols, cap, dual=(tau, col_cnt, col_buf, col_cap))
-            else:
-                splits = lib.lib.kb2_suggest_splits(rows.n, cols.n, cap, sm)
-                cand_rows = torch.empty((rows.n, splits * cap), dtype=torch.int32, device=dev)
-                if prof is not None:
-                    ev0 = torch.cuda.Event(enable_timing=True)
-                    ev0.record()
-                lib.call("kb2_knn_fused", lib.ptr(rows.hi), lib.ptr(rows.lo), lib.ptr(rows.key), rows.n,
-                         lib.ptr(cols.hi), lib.ptr(cols.lo), lib.ptr(cols.key), cols.n, rows.dpad, cap,
-                         splits, lib.ptr(tau), lib.ptr(col_cnt), lib.ptr(col_buf), col_cap,
-                         lib.ptr(cand_rows), st)
-                if prof is not None:
-                    ev1 = torch.cuda.Event(enable_timing=True)
-                    ev1.record()
-                    prof.append((ev0, ev1, rows.n, cols.n, rows.d, "tf32x3-dual"))
-            # 3. row side: exact finish of the row lists
-            if screen:
-                fwd_d, fwd_i, unv = self._refine_checked(
-                    rows, cols, cand_rows, k_rows, exclude_self_rows,
-                    lib.ptr(key_rows) + 4 * (cap - 1), r_lists * cap, cap, r_lists)
                 self.search_stats["screen_rows"] += rows.n
-                self._research(rows, cols, torch.nonzero(unv).flatten(), k_rows, exclude_self_rows,
-                               fwd_d, fwd_i)
-                fwd = (fwd_d, fwd_i)
-                del key_rows
-            else:
-                fwd = self._refine(rows, cols, cand_rows, k_rows, exclude_self_rows)
-            # 4. column side: best cap emitted rows per column, exact finish
+                self._research(rows, cols, torch.nonzero(unv_rows).flatten(), k_rows,
+                               exclude_self_rows, fwd_d, fwd_i)
+            fwd = (fwd_d, fwd_i)
+            # 3. column side: best cap emitted rows per column, exact finish
             cand_cols = torch.empty((cols.n, cap), dtype=torch.int32, device=dev)
             overflow = torch.empty(cols.n, dtype=torch.int32, device=dev)
             col_tau = torch.empty(cols.n, dtype=torch.float32, device=dev) if screen else None
@@ -538,18 +587,22 @@ class B200Mixin:
                     rev_d[bad] = d_b
                     rev_i[bad] = i_b
             if prof is not None:
+                emitted += torch.where(col_cnt < (1 << 30), col_cnt, 0).sum()
                 self._fused_stats = {"sample_rows": int(n_s), "col_cap": int(col_cap),
-                                     "emitted_per_column_mean": float(col_cnt.float().mean()),
-                                     "emitted_per_column_max": int(col_cnt.max()),
+                                     "row_segments": [int(b) for b in bounds],
+                                     "emitted_per_column_mean": float(emitted) / max(1, cols.n),
                                      "overflow_columns": n_over}
         return fwd, (rev_d, rev_i)
 
-    def _refine(self, q: PreparedRows, y: PreparedRows, cand, k: int, exclude_self: bool):
+    def _refine(self, q: PreparedRows, y: PreparedRows, cand, k: int, exclude_self: bool, out=None):
         """Exact float64 finish of candidate lists `cand` (local ids into y)."""
         lib = self._lib
         dev = self.device
-        out_d = torch.empty((q.n, k), dtype=torch.float64, device=dev)
-        out_i = torch.empty((q.n, k), dtype=torch.int64, device=dev)
+        if out is not None:
+            out_d, out_i = out
+        else:
+            out_d = torch.empty((q.n, k), dtype=torch.float64, device=dev)
+            out_i = torch.empty((q.n, k), dtype=torch.int64, device=dev)
         q_raw, y_raw = q.raw, y.raw
         if q_raw.dtype != y_raw.dtype:
             q_raw, y_raw = q_raw.to(torch.float64), y_raw.to(torch.float64)

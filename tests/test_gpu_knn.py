@@ -186,6 +186,41 @@ def test_fused_column_overflow_falls_back(impl):
     O.assert_neighbors_match(rd.cpu().numpy(), ri.cpu().numpy(), want_d, want_i, RTOL, ATOL, what="rev")
 
 
+@pytest.mark.parametrize("impl", ["tc", "screen"])
+@pytest.mark.parametrize("single", [False, True])
+@pytest.mark.parametrize("col_cap", [512, 24])
+def test_fused_row_segments_tighten_thresholds(impl, single, col_cap):
+    """The dual-direction pass in row segments with kb2_col_compact between them (thresholds
+    tighten, buffers are compacted; col_cap = 24 forces sticky overflows across segments):
+    same results as the oracle in both directions."""
+    nq, ny, d, c = 5000, 1500, 64, 10
+    q, y = _data(nq, ny, d, seed=77)
+    if single:
+        y, ny = q, nq
+    algo = _algo(n_candidates=c, fused=True, impl=impl)
+    algo.FUSED_SEGMENT_MIN_ROWS = 256
+    algo.FUSED_SAMPLE_DIV = 32.0
+    algo.FUSED_COL_CAP = col_cap
+    algo._profile = []                       # collect _fused_stats
+    qp = algo._prepare(q, cache=False)
+    yp = qp if single else algo._prepare(y, cache=False)
+    k_fwd = c
+    (fd, fi), (rd, ri) = algo.search_both(qp, yp, k_fwd, c, exclude_self_rows=single)
+    stats = algo._fused_stats
+    assert len(stats["row_segments"]) >= 5, stats
+    if col_cap == 512:
+        assert stats["overflow_columns"] == 0
+        # one threshold from the sample alone would emit ~cap * 32 = 512 rows per column
+        assert stats["emitted_per_column_mean"] < 200, stats
+    else:
+        assert stats["overflow_columns"] > 0
+    q64, y64 = q.astype(np.float64), y.astype(np.float64)
+    want_d, want_i = O.knn_brute(q64, y64, k_fwd, "euclidean", exclude_self=single)
+    O.assert_neighbors_match(fd.cpu().numpy(), fi.cpu().numpy(), want_d, want_i, RTOL, ATOL, what="fwd")
+    want_d, want_i = O.knn_brute(y64, q64, c, "euclidean")
+    O.assert_neighbors_match(rd.cpu().numpy(), ri.cpu().numpy(), want_d, want_i, RTOL, ATOL, what="rev")
+
+
 # ---------------------------------------------------------------------------
 # the 1xTF32 screen: proposals + float64 completeness proof + 3xTF32 re-search
 # ---------------------------------------------------------------------------
