@@ -86,16 +86,15 @@ __device__ __forceinline__ void load_taucol(const float *__restrict__ tau_col, i
 // One accumulator tile (this warp's 32 TMEM lanes x BN columns), column side.
 // `tk` = this warp's shared copy of the tile's thresholds, xk = x_key of this thread's row
 // (+inf for rows that do not exist: they never emit), row_base = row of lane 0.
-template <int BN>
+// DOUBLE_BUFFER: the next chunk's tcgen05.ld is in flight while this one is tested (needs the
+// register budget of setmaxnreg, see knn_screen.cu).
+template <int BN, bool DOUBLE_BUFFER = false>
 __device__ __forceinline__ void column_tile(const FusedParams &FP, EmitQueue &Q, const float *tk,
                                             uint32_t taddr, int64_t c0, float xk, int64_t row_base,
                                             int lane) {
+    constexpr int NCH = BN / 32;
     const float nxk = -xk;
-#pragma unroll 1
-    for (int ch = 0; ch < BN / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr + ch * 32, r);
-        tmem_ld_wait();
+    auto process = [&](const uint32_t (&r)[32], int ch) {
         // g = -2 acc - tau_col;  emit when  key_x - 2 acc < tau_col  <=>  g < -key_x
         float g[32];
 #pragma unroll
@@ -108,7 +107,7 @@ __device__ __forceinline__ void column_tile(const FusedParams &FP, EmitQueue &Q,
             for (int j = 1; j < 8; ++j) m4[q] = fminf(m4[q], g[8 * q + j]);
         }
         const float gmin = fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
-        if (!__any_sync(FULL_MASK, gmin < nxk)) continue;
+        if (!__any_sync(FULL_MASK, gmin < nxk)) return;
         // Survivors go to the warp's queue (ballot-ranked, no atomics); the queue is drained
         // 17-48 entries at a time so that the global atomics that assign the column-buffer
         // slots are in flight together instead of one latency each.
@@ -133,6 +132,27 @@ __device__ __forceinline__ void column_tile(const FusedParams &FP, EmitQueue &Q,
                 if (Q.n > EMIT_Q - 32) emit_flush(FP, Q, row_base, lane);
             }
         }
+    };
+    uint32_t ra[32];
+    if constexpr (!DOUBLE_BUFFER) {
+#pragma unroll 1
+        for (int ch = 0; ch < NCH; ++ch) {
+            tmem_ld_32x32b_x32(taddr + ch * 32, ra);
+            tmem_ld_wait();
+            process(ra, ch);
+        }
+        return;
+    }
+    uint32_t rb[32];
+    tmem_ld_32x32b_x32(taddr, ra);
+#pragma unroll 1
+    for (int ch = 0; ch < NCH; ch += 2) {
+        tmem_ld_wait();
+        tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, rb);   // in flight while ra is tested
+        process(ra, ch);
+        tmem_ld_wait();
+        if (ch + 2 < NCH) tmem_ld_32x32b_x32(taddr + (ch + 2) * 32, ra);
+        process(rb, ch + 1);
     }
 }
 

@@ -38,6 +38,18 @@ constexpr int S_HALF = 128;      // ... of which each CTA stages 128
 constexpr int S_BK = 32;         // K chunk: 128-byte swizzle rows
 constexpr int S_MAX_DPAD = 256;  // resident query tile: 128 rows x dpad fp32 <= 128 KB
 
+// Dual-direction form: 384 threads share the 64 K registers (168 each).  Experiment kept behind
+// a macro (off): the producer / MMA warpgroup (warps 8-11) gives registers to the two epilogue
+// warpgroups (setmaxnreg 56 / 224), which then keep the next chunk's tcgen05.ld in flight while
+// they test the current one, like the one-direction kernel.  Measured 49 % SLOWER at C4
+// (1402 vs 940 ms per step, profiles/r01_ab_experiments.md block I): two epilogue warps per
+// scheduler already hide the TMEM latency, and ptxas parks loop invariants on the stack around
+// setmaxnreg.
+#ifndef KB2_DUAL_SETMAXNREG
+#define KB2_DUAL_SETMAXNREG 0
+#endif
+constexpr bool DUAL_REGS = KB2_DUAL_SETMAXNREG != 0;
+
 struct ScreenParams {
     int64_t nq, ny;
     int kchunks, cap, buf_slots, stages;
@@ -140,6 +152,9 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap map_q,
     const uint32_t full_u32 = smem_u32(full_bar), empty_u32 = smem_u32(empty_bar);
     const uint32_t tmem_empty_leader = smem_u32(tmem_empty) & PEER_BIT_MASK;
 
+    if (warp >= EPI_WARPS) {
+    // producer / MMA warpgroup (DUAL: + two idle warps): 128 x 56 + 256 x 224 = 64 512 registers
+    if constexpr (DUAL && DUAL_REGS) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == PROD_WARP) {
         // ------------------------------------------------------ TMA producer (both CTAs)
         int stage = 0;
@@ -217,7 +232,10 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap map_q,
                 }
             }
         }
-    } else if (warp < 4) {
+    }
+    } else {
+    if constexpr (DUAL && DUAL_REGS) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    if (warp < 4) {
         // ------------------------------------------------------ row epilogue, both CTAs
         const int lrow = warp * 32 + lane;
         float *yk = tile_s + warp * BN;
@@ -277,7 +295,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap map_q,
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
-                epilogue_tile<BN, !DUAL>(L, lrow, yk, taddr, c0, tau, cnt, lane);
+                epilogue_tile<BN, !DUAL || DUAL_REGS>(L, lrow, yk, taddr, c0, tau, cnt, lane);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(tmem_empty_leader + (uint32_t)acc * 8);
@@ -302,7 +320,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap map_q,
             }
             __syncwarp();
         }
-    } else if (DUAL && warp < 8) {
+    } else if (DUAL) {
         // ------------------------------------------------------ column epilogue, both CTAs
         const int quad = warp - 4;                         // TMEM lane quadrant
         const int lrow = quad * 32 + lane;
@@ -334,7 +352,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap map_q,
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-                column_tile<BN>(FP, Q, tk, taddr, c0, xk, row_base, lane);
+                column_tile<BN, DUAL_REGS>(FP, Q, tk, taddr, c0, xk, row_base, lane);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(tmem_empty_leader + (uint32_t)acc * 8);
@@ -343,6 +361,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap map_q,
             while (Q.n > 0) emit_flush(FP, Q, row_base, lane);   // rows change with the unit
         }
         emit_retire(FP, Q);                                      // the last drain's entries
+    }
     }
 
     // no CTA may exit (or free TMEM) while its peer can still signal its barriers
