@@ -87,3 +87,27 @@ def test_sass_is_blackwell_native():
     assert "UTCHMMA" in sass or "UTCMMA" in sass
     assert "LDTM" in sass and "UTMALDG" in sass
     assert "HMMA.16816" not in sass          # no legacy mma.sync path
+
+
+def test_integration_stub_calls_match_the_header_arity():
+    """The reference-side binding documented in INTEGRATION.md section 2 passes as many
+    arguments to each entry point as include/kiez_b200.h declares (the GPU suite executes it)."""
+    from kiez_b200 import _lib
+
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    section = text[text.index("## 2. The minimal stub"):]
+    code = re.search(r"```python\n(.*?)```", section, re.S).group(1)
+    compile(code, "INTEGRATION.md#stub", "exec")
+    for name in ("kb2_prepare_rows", "kb2_knn_candidates", "kb2_refine_topk"):
+        call = code[code.index("_lib." + name + "("):]
+        depth, n_args = 0, 1
+        for ch in call[call.index("(") + 1:]:
+            if ch in "([":
+                depth += 1
+            elif ch in ")]":
+                if depth == 0:
+                    break
+                depth -= 1
+            elif ch == "," and depth == 0:
+                n_args += 1
+        assert n_args == len(_lib.SIGNATURES[name]), name
