@@ -108,29 +108,41 @@ __device__ __forceinline__ void column_tile(const FusedParams &FP, EmitQueue &Q,
         }
         const float gmin = fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
         if (!__any_sync(FULL_MASK, gmin < nxk)) return;
-        // Survivors go to the warp's queue (ballot-ranked, no atomics); the queue is drained
-        // 17-48 entries at a time so that the global atomics that assign the column-buffer
-        // slots are in flight together instead of one latency each.
+        // Slow path (some lane has a survivor).  Every emit used to cost the CTA pair a chain of
+        // ~13 dependent warp votes (8 groups, 4 ballots each where one passed), and a late
+        // epilogue warp holds the accumulator buffer of all 16.  Now: each lane builds its own
+        // 32-bit pass mask without votes; per round ONE ballot ranks the lanes that still hold
+        // a survivor and each of them queues its lowest one (r[j] with a runtime j comes from a
+        // 5-level select tree, not local memory).  Rounds = most survivors in one lane, almost
+        // always 1.  The queue is drained 17-48 entries at a time so that the global atomics
+        // that assign the column-buffer slots are in flight together.
+        unsigned int m = 0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            bool any_pass = false;
+        for (int j = 0; j < 32; ++j) m |= (g[j] < nxk) ? (1u << j) : 0u;
+        for (;;) {
+            const bool have = m != 0;
+            const unsigned int has = __ballot_sync(FULL_MASK, have);
+            if (has == 0) break;
+            if (have) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                uint32_t s16[16], s8[8], s4[4], s2[2];
 #pragma unroll
-            for (int j = 4 * q; j < 4 * q + 4; ++j) any_pass |= (g[j] < nxk);
-            if (!__any_sync(FULL_MASK, any_pass)) continue;
+                for (int i = 0; i < 16; ++i) s16[i] = (j & 16) ? r[i + 16] : r[i];
 #pragma unroll
-            for (int j = 4 * q; j < 4 * q + 4; ++j) {
-                const bool pass = g[j] < nxk;
-                const unsigned mask = __ballot_sync(FULL_MASK, pass);
-                if (mask == 0) continue;
-                if (pass) {
-                    const int slot = Q.n + __popc(mask & ((1u << lane) - 1));
-                    Q.key[slot] = fmaf(-2.f, __uint_as_float(r[j]), xk);
-                    Q.col[slot] = (int)(c0 + ch * 32 + j);
-                    Q.lane[slot] = (unsigned char)lane;
-                }
-                Q.n += __popc(mask);
-                if (Q.n > EMIT_Q - 32) emit_flush(FP, Q, row_base, lane);
+                for (int i = 0; i < 8; ++i) s8[i] = (j & 8) ? s16[i + 8] : s16[i];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) s4[i] = (j & 4) ? s8[i + 4] : s8[i];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) s2[i] = (j & 2) ? s4[i + 2] : s4[i];
+                const uint32_t val = (j & 1) ? s2[1] : s2[0];
+                const int slot = Q.n + __popc(has & ((1u << lane) - 1));
+                Q.key[slot] = fmaf(-2.f, __uint_as_float(val), xk);
+                Q.col[slot] = (int)(c0 + ch * 32 + j);
+                Q.lane[slot] = (unsigned char)lane;
             }
+            Q.n += __popc(has);
+            if (Q.n > EMIT_Q - 32) emit_flush(FP, Q, row_base, lane);
         }
     };
     uint32_t ra[32];

@@ -230,6 +230,35 @@ __device__ __forceinline__ void select_chunk(const RowLists &L, int row, const f
     const float mn = fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
     if (!__any_sync(FULL_MASK, mn < tau)) return;
     ent_t *buf = L.ent + (size_t)row * L.stride + L.cap;
+    if constexpr (NV == 32) {
+        // Sparse chunk (the steady state: a fraction of a survivor per 32 x 32 chunk): every
+        // lane's survivors fit its buffer, so they are appended without the per-group votes --
+        // 3 votes per passing chunk instead of 10.  v[j] with a runtime j comes from a 5-level
+        // select tree (no local memory).  Dense chunks (list fill phase) take the loop below.
+        unsigned int m = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m |= (v[j] < tau) ? (1u << j) : 0u;
+        if (!__any_sync(FULL_MASK, cnt + __popc(m) > L.B)) {
+            while (m) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                float s16[16], s8[8], s4[4], s2[2];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) s16[i] = (j & 16) ? v[i + 16] : v[i];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s8[i] = (j & 8) ? s16[i + 8] : s16[i];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) s4[i] = (j & 4) ? s8[i + 4] : s8[i];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) s2[i] = (j & 2) ? s4[i + 2] : s4[i];
+                buf[cnt] = pack_entry((j & 1) ? s2[1] : s2[0], col0 + j);
+                ++cnt;
+            }
+            const bool full = cnt > L.B - LISTS_GROUP;
+            if (__any_sync(FULL_MASK, full)) merge_rows(L, row, tau, cnt, full, lane);
+            return;
+        }
+    }
 #pragma unroll
     for (int g = 0; g < NV / LISTS_GROUP; ++g) {
         // most groups of a passing chunk still hold no survivor: skip them with one vote
