@@ -17,7 +17,6 @@ import os
 import statistics
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -94,38 +93,41 @@ def synth(n, d, seed, device):
 # clocks sampling (B200_PROFILING.md "clocks line")
 # ---------------------------------------------------------------------------
 class ClockSampler:
+    """ONE `nvidia-smi -lms 200` process for the whole timed region (the recipe's form): spawning
+    nvidia-smi per sample initialises NVML every 200 ms and measurably perturbs the step."""
+
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
         self.index = index
-        self.samples = []
-        self._stop = threading.Event()
-        self._thr = None
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(
-                    ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                     "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                self.samples.append([x.strip() for x in out.strip().split(",")])
-            except Exception:
-                pass
-            self._stop.wait(0.2)
+        self._proc = None
 
     def start(self):
-        self._thr = threading.Thread(target=self._run, daemon=True)
-        self._thr.start()
+        try:
+            self._proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self._proc = None
 
     def stop(self):
-        self._stop.set()
-        if self._thr:
-            self._thr.join(timeout=6)
+        out = ""
+        if self._proc is not None:
+            try:
+                self._proc.terminate()
+                out, _ = self._proc.communicate(timeout=10)
+            except Exception:
+                try:
+                    self._proc.kill()
+                except Exception:
+                    pass
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        for line in out.splitlines():
+            s = [x.strip() for x in line.split(",")]
             try:
                 sm.append(float(s[0]))
                 mx.append(float(s[1]))
@@ -280,9 +282,10 @@ def run_b200(args, w):
 
     out_algo = []
 
-    def step(src, tgt, profile=None):
+    def step(src, tgt, profile=None, collect_stats=False):
         inst = make()
         inst.algorithm._profile = profile
+        inst.algorithm._collect_stats = collect_stats
         out_algo[:] = [inst.algorithm]
         inst.fit(src, tgt)
         dist_, ind_ = inst.kneighbors(w["k"])
@@ -349,6 +352,10 @@ def run_b200(args, w):
         achieved = by_kind[kind]["flop"] / (top_ms * 1e-3) / 1e12
     else:
         top_ms, top_n, top_flop, achieved, kind = 0.0, 0, 0.0, 0.0, "tf32x3"
+    # emit / overflow statistics of the dual-direction pass need extra reductions and host
+    # syncs: gathered in one more step OUTSIDE the timed region
+    step(source, target, collect_stats=True)
+    barrier()
     fused_stats = getattr(out_algo[0], "_fused_stats", None) if out_algo else None
     search_stats = dict(getattr(out_algo[0], "search_stats", {})) if out_algo else {}
     mmas = 1.0 if kind.startswith("screen") else 3.0      # MMAs issued per algorithmic MAC

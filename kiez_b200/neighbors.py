@@ -286,7 +286,15 @@ class B200Mixin:
         """C-contiguous rows on this backend's device: fp32 (the production dtype), or
         float64 when the caller passes float64 (the README example does), in which case
         the candidate search still runs on the fp32-rounded split but the exact finish
-        reads the caller's float64 values."""
+        reads the caller's float64 values.
+
+        Distributed mode, host input: every rank holds the same host array (the contract of
+        INTEGRATION.md section 4), so each rank uploads only its 1/world slice over PCIe and
+        the slices are exchanged with one NCCL all-gather over NVLink -- world x less
+        host-to-device traffic per rank than every rank uploading the whole matrix."""
+        on_host = isinstance(data, np.ndarray) or not data.is_cuda
+        if on_host and self.distributed and data.ndim == 2 and data.shape[0] >= 4096:
+            return self._upload_sharded(data)
         if isinstance(data, np.ndarray):
             keep64 = data.dtype == np.float64
             t = torch.from_numpy(np.ascontiguousarray(
@@ -295,6 +303,27 @@ class B200Mixin:
         keep64 = data.dtype == torch.float64
         return data.to(device=self.device,
                        dtype=torch.float64 if keep64 else torch.float32).contiguous()
+
+    def _upload_sharded(self, data):
+        import torch.distributed as dist
+
+        world, rank = dist.get_world_size(), dist.get_rank()
+        n, d = data.shape
+        per = -(-n // world)
+        lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
+        if isinstance(data, np.ndarray):
+            dtype = torch.float64 if data.dtype == np.float64 else torch.float32
+            part = torch.from_numpy(np.ascontiguousarray(
+                data[lo:hi], dtype=np.float64 if dtype == torch.float64 else np.float32))
+        else:
+            dtype = torch.float64 if data.dtype == torch.float64 else torch.float32
+            part = data[lo:hi].to(dtype).contiguous()
+        full = torch.empty((world * per, d), dtype=dtype, device=self.device)
+        mine = torch.zeros((per, d), dtype=dtype, device=self.device) if hi - lo < per else \
+            torch.empty((per, d), dtype=dtype, device=self.device)
+        mine[: hi - lo].copy_(part, non_blocking=True)
+        dist.all_gather_into_tensor(full, mine)
+        return full[:n]
 
     def _prepare(self, data, cache: bool) -> PreparedRows:
         hit = self._prepared.get(id(data))
@@ -437,7 +466,7 @@ class B200Mixin:
     # instead of cap * DIV from one threshold.  Measured at C4 the pass costs ~1.2 ms per emitted
     # row per column (profiles/r01_ab_experiments.md block H).  KB2_FUSED_* override for tuning.
     FUSED_SAMPLE_DIV = float(os.environ.get("KB2_FUSED_SAMPLE_DIV", "32"))
-    FUSED_SEGMENT_GROWTH = float(os.environ.get("KB2_FUSED_GROWTH", "2"))     # <= 1: one segment
+    FUSED_SEGMENT_GROWTH = float(os.environ.get("KB2_FUSED_GROWTH", "3"))     # <= 1: one segment
     FUSED_SEGMENT_MIN_ROWS = int(os.environ.get("KB2_FUSED_MIN_ROWS", "16384"))
     FUSED_COL_CAP = int(os.environ.get("KB2_FUSED_COL_CAP", "512"))          # slots per column buffer
 
@@ -523,7 +552,9 @@ class B200Mixin:
             fwd_i = torch.empty((rows.n, k_rows), dtype=torch.int64, device=dev)
             unv_rows = torch.empty((rows.n,), dtype=torch.int32, device=dev) if screen else None
             bounds = self._fused_segments(rows.n, n_s)
-            emitted = torch.zeros((), dtype=torch.int64, device=dev) if prof is not None else None
+            # statistics for bench.py / tests (extra reductions and host syncs): only on request
+            stats = bool(getattr(self, "_collect_stats", False))
+            emitted = torch.zeros((), dtype=torch.int64, device=dev) if stats else None
             for lo, hi in zip(bounds[:-1], bounds[1:]):
                 seg = rows.rows(lo, hi)
                 if screen:
@@ -574,7 +605,7 @@ class B200Mixin:
                 rev_d, rev_i, unv = self._refine_checked(cols, rows, cand_cols, k_cols, False,
                                                          lib.ptr(col_tau), 1, 1, 1)
                 self.search_stats["screen_rows"] += cols.n
-                n_over = int(overflow.sum()) if prof is not None else 0
+                n_over = int(overflow.sum()) if stats else 0
                 # overflowed columns lost rows below their threshold: search them again too
                 self._research(cols, rows, torch.nonzero(unv | overflow).flatten(), k_cols, False,
                                rev_d, rev_i)
@@ -586,7 +617,7 @@ class B200Mixin:
                     d_b, i_b = self._search_tf32x3(cols.take(bad), rows, k_cols)
                     rev_d[bad] = d_b
                     rev_i[bad] = i_b
-            if prof is not None:
+            if stats:
                 emitted += torch.where(col_cnt < (1 << 30), col_cnt, 0).sum()
                 self._fused_stats = {"sample_rows": int(n_s), "col_cap": int(col_cap),
                                      "row_segments": [int(b) for b in bounds],

@@ -63,3 +63,25 @@ def test_two_gpu_matches_oracle(hub, kw, label, single, fused):
     for rank in range(2):
         d, i = out[rank]
         O.assert_neighbors_match(d, i, want_d, want_i, 1e-5, 5e-6, what=f"{label} rank{rank}")
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_two_gpu_sharded_upload(fused, dtype):
+    """Host inputs of >= 4096 rows: every rank uploads its slice, NCCL all-gathers the matrix
+    (B200._upload_sharded); row counts that do not divide by the world size."""
+    import torch.multiprocessing as mp
+
+    rng = np.random.default_rng(32)
+    source = rng.standard_normal((4099, 32)).astype(dtype)
+    target = rng.standard_normal((5001, 32)).astype(dtype)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), source, target, "CSLS", {}, 10, 5, out, fused),
+             nprocs=2, join=True)
+    want_d, want_i = O.kiez_kneighbors(source.astype(np.float64), target.astype(np.float64),
+                                       hubness="csls", n_candidates=10, k=5)
+    for rank in range(2):
+        d, i = out[rank]
+        O.assert_neighbors_match(d, i, want_d, want_i, 1e-5, 5e-6, what=f"sharded upload rank{rank}")

@@ -201,7 +201,7 @@ def test_fused_row_segments_tighten_thresholds(impl, single, col_cap):
     algo.FUSED_SEGMENT_MIN_ROWS = 256
     algo.FUSED_SAMPLE_DIV = 32.0
     algo.FUSED_COL_CAP = col_cap
-    algo._profile = []                       # collect _fused_stats
+    algo._collect_stats = True
     qp = algo._prepare(q, cache=False)
     yp = qp if single else algo._prepare(y, cache=False)
     k_fwd = c

@@ -1,0 +1,7 @@
+#!/bin/bash
+# 2 GPUs: sharded upload (each rank uploads 1/world of a host matrix + NCCL all-gather): tests + e2e
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_distributed.py -m gpu -q -x --timeout 600 > gpurun_out/pytest_dist.log 2>&1; echo "pytest(dist) exit $?"; tail -3 gpurun_out/pytest_dist.log
+N=2
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus $N --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/b_c4_${N}gpu.json 2> gpurun_out/b_c4_${N}gpu.err; echo "bench ${N}gpu exit $?"; python -c "
+import json; d=json.load(open('gpurun_out/b_c4_${N}gpu.json')); r=d['roofline']; print('${N}gpu', 'q/s', round(d['value']), 'ms/step', round(d['ms_per_step'],1), 'top ms/step', round(r['avg_launch_ms']*r['launches']/d['steps'],1), 'frac', round(r['frac'],3), d['clocks'], d['e2e'], [round(s['avg_launch_ms'],1) for s in r['search_launches']])"; tail -2 gpurun_out/b_c4_${N}gpu.err | cut -c1-300

@@ -1,0 +1,69 @@
+"""Where does a C4 step spend GPU time OUTSIDE kernels?  Runs warm-up steps, then one step under
+torch.profiler (CUPTI), and prints the idle gaps between consecutive kernels on the device.
+
+    python tools/trace_step.py [--n 1000000 --m 1000000 --d 256 --c 10 --k 10] > gpurun_out/trace.txt
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch
+from torch.profiler import ProfilerActivity, profile
+
+from kiez_b200 import B200, Kiez
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--m", type=int, default=1_000_000)
+    ap.add_argument("--d", type=int, default=256)
+    ap.add_argument("--c", type=int, default=10)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--min-gap-us", type=float, default=200.0)
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev)
+    g.manual_seed(0)
+    src = torch.randn((args.n, args.d), generator=g, device=dev)
+    g.manual_seed(1)
+    tgt = torch.randn((args.m, args.d), generator=g, device=dev)
+
+    def step():
+        inst = Kiez(n_candidates=args.c, algorithm=B200(n_candidates=args.c), hubness="CSLS")
+        inst.fit(src, tgt)
+        return inst.kneighbors(args.k)
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        step()
+        torch.cuda.synchronize()
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    evs.sort(key=lambda e: e.time_range.start)
+    if not evs:
+        print("no CUDA events recorded")
+        return
+    t0, t1 = evs[0].time_range.start, max(e.time_range.end for e in evs)
+    busy = sum(e.time_range.end - e.time_range.start for e in evs)
+    print(f"step span {1e-3 * (t1 - t0):.1f} ms, kernels+memops busy {1e-3 * busy:.1f} ms, "
+          f"idle {1e-3 * (t1 - t0 - busy):.1f} ms, {len(evs)} device activities")
+    print(f"gaps >= {args.min_gap_us:.0f} us (after -> before):")
+    end = evs[0].time_range.end
+    prev = evs[0]
+    for e in evs[1:]:
+        gap = e.time_range.start - end
+        if gap >= args.min_gap_us:
+            print(f"  {1e-3 * gap:8.2f} ms   t={1e-3 * (end - t0):8.1f} ms   {prev.name[:60]:<60s} -> {e.name[:60]}")
+        if e.time_range.end > end:
+            end, prev = e.time_range.end, e
+    print("largest device activities:")
+    for e in sorted(evs, key=lambda e: e.time_range.start - e.time_range.end)[:12]:
+        print(f"  {1e-3 * (e.time_range.end - e.time_range.start):8.2f} ms  {e.name[:90]}")
+
+
+if __name__ == "__main__":
+    main()
