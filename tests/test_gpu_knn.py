@@ -199,6 +199,7 @@ def test_fused_row_segments_tighten_thresholds(impl, single, col_cap):
         y, ny = q, nq
     algo = _algo(n_candidates=c, fused=True, impl=impl)
     algo.FUSED_SEGMENT_MIN_ROWS = 256
+    algo.FUSED_SEGMENT_GROWTH = 2.0
     algo.FUSED_SAMPLE_DIV = 32.0
     algo.FUSED_COL_CAP = col_cap
     algo._collect_stats = True
