@@ -405,9 +405,11 @@ def run_b200(args, w):
             t = torch.tensor([t_e2e], device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             t_e2e = float(t.item())
+        # whole-job bytes: with N ranks every rank uploads its 1/N slice of both matrices
+        # (B200._upload_sharded; the rest arrives over NVLink) and downloads the full result
         e2e = {"value": w["n"] / t_e2e, "unit": "queries/s",
                "h2d_bytes_per_step": int(src_h.nbytes + tgt_h.nbytes),
-               "d2h_bytes_per_step": int(d_.nbytes + i_.nbytes), "steps": n_e2e,
+               "d2h_bytes_per_step": int(d_.nbytes + i_.nbytes) * world, "steps": n_e2e,
                "timer": "host wall clock around fit+kneighbors incl. copies, max over ranks"}
 
     cpu = None

@@ -51,6 +51,7 @@ def _rows_on_device(algo, data, cache):
     return _as_device(data, _device_of(algo), torch.float32)
 
 
+
 class HubnessReduction(ABC):
     """hubness_reduction/base.py:17-105."""
 
@@ -121,6 +122,8 @@ class HubnessReduction(ABC):
     def _finish(self, dist, ind):
         """Mirror the caller's container type: numpy in -> numpy out (like Faiss+numpy)."""
         if getattr(self.nn_algo, "_input_is_numpy", False):
+            # (pinned staging buffers were tried: the first-call cudaHostAlloc costs more than the
+            # pageable copy of an (n, k) result saves)
             return dist.cpu().numpy(), ind.cpu().numpy()
         return dist, ind
 

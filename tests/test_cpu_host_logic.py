@@ -145,3 +145,57 @@ def test_candidate_capacity_and_shard_bounds():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+class _SegmentKnobs:
+    """The class-level knobs `_fused_segments` / `_fused_sample_rows` read (no device needed)."""
+
+    FUSED_SAMPLE_DIV = 32.0
+    FUSED_SEGMENT_GROWTH = 3.0
+    FUSED_SEGMENT_MIN_ROWS = 16384
+    FUSED_COL_CAP = 512
+
+
+@pytest.mark.parametrize(("n_rows", "growth", "min_rows"), [
+    (1_000_000, 3.0, 16384), (1_000_000, 2.0, 16384), (1_000_000, 1.5, 16384), (5000, 2.0, 256),
+    (300, 2.0, 16384), (257, 2.0, 256), (1, 3.0, 256), (999_999, 4.0, 1000), (1_000_000, 1.0, 16384)])
+def test_fused_row_segments_cover_the_rows(n_rows, growth, min_rows):
+    """Row segments of the dual-direction pass (B200._fused_segments): contiguous, cover every
+    row once, start on tile-pair boundaries, grow geometrically, no short tail."""
+    from kiez_b200.neighbors import B200Mixin
+
+    knobs = _SegmentKnobs()
+    knobs.FUSED_SEGMENT_GROWTH, knobs.FUSED_SEGMENT_MIN_ROWS = growth, min_rows
+    n_s = B200Mixin._fused_sample_rows(knobs, n_rows, 16)
+    assert 1 <= n_s <= n_rows
+    assert n_s == n_rows or n_s >= 8 * 16
+    bounds = B200Mixin._fused_segments(knobs, n_rows, n_s)
+    assert bounds[0] == 0 and bounds[-1] == n_rows
+    sizes = np.diff(bounds)
+    assert (sizes > 0).all()
+    assert all(b % 256 == 0 for b in bounds[:-1])
+    if growth <= 1.0:
+        assert bounds == [0, n_rows]
+    else:
+        # each segment is about (growth - 1) x everything seen before it (sample included)
+        seen = n_s
+        for lo, hi in zip(bounds[:-2], bounds[1:-1]):
+            want = max(int((growth - 1.0) * seen), min_rows, 256)
+            assert want <= hi - lo < want + 256
+            seen += hi - lo
+        # expected emits per column ~ cap * sum(segment / seen-before): logarithmic in n / n_s
+        seen, emits = n_s, 0.0
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
+            emits += (hi - lo) / seen
+            seen += hi - lo
+        assert emits <= (growth - 1.0) * (np.log(max(n_rows / n_s, 1.0)) / np.log(growth) + 2.5) + 1e-9 \
+            or n_rows <= min_rows * 4
+
+
+def test_fused_col_cap_follows_the_list_length():
+    from kiez_b200.neighbors import B200Mixin
+
+    knobs = _SegmentKnobs()
+    assert B200Mixin._fused_col_cap(knobs, 16) == 512
+    knobs.FUSED_COL_CAP = 16
+    assert B200Mixin._fused_col_cap(knobs, 56) == 56

@@ -198,3 +198,54 @@ def test_full_size_properties_c4_like():
                              RTOL, ATOL, what="c4-like sample")
     scores = hubness_score(ind, m, k=k, store_k_occurrence=True)
     assert int(scores["k_occurrence"].sum()) == n * k          # checksum of the histogram
+
+
+def test_full_size_c4_sampled_parity():
+    """BASELINE.json's metric configuration at FULL size (C4: 1M x 1M, d=256, c=k=10, CSLS) through
+    the default path -- 1xTF32 screen + proof, dual-direction pass in row segments: oracle parity
+    on sampled rows of BOTH directions, plus the size-independent properties (sortedness, id
+    range, no duplicates, histogram checksum).  The oracle side uses the scikit-learn brute-force
+    call the reference makes, on float64 copies of the same values."""
+    from kiez_b200 import B200, Kiez, hubness_score
+
+    free, _total = torch.cuda.mem_get_info()
+    if free < 40 * (1 << 30):
+        pytest.skip("needs 40 GB of free device memory")
+    n = m = 1_000_000
+    d, c, k = 256, 10, 10
+    g = torch.Generator(device="cuda")
+    g.manual_seed(0)
+    source = torch.randn((n, d), generator=g, device="cuda")
+    g.manual_seed(1)
+    target = torch.randn((m, d), generator=g, device="cuda")
+    inst = Kiez(n_candidates=c, algorithm=B200(n_candidates=c), hubness="CSLS")
+    inst.fit(source, target)
+    algo = inst.algorithm
+    assert algo._fused_forward is not None, "C4 must take the dual-direction pass by default"
+    assert algo.search_stats["screen_rows"] == n + m, "C4 must take the 1xTF32 screen by default"
+    assert algo.search_stats["screen_unverified"] < 0.01 * (n + m)
+    dist, ind = inst.kneighbors(k)
+    assert (torch.diff(dist, dim=1) >= 0).all()
+    assert int(ind.min()) >= 0 and int(ind.max()) < m
+    srt = torch.sort(ind, dim=1).values
+    assert (srt[:, 1:] != srt[:, :-1]).all()
+    rev_dist, rev_ind = inst.hubness.r_dist_train_, inst.hubness.r_ind_train_
+    assert (torch.diff(rev_dist, dim=1) >= 0).all()
+    assert int(rev_ind.min()) >= 0 and int(rev_ind.max()) < n
+    # oracle on a row sample (rows from every row segment of the pass)
+    rows = np.sort(np.random.default_rng(1).choice(n, 48, replace=False))
+    s64 = source.cpu().numpy().astype(np.float64)
+    t64 = target.cpu().numpy().astype(np.float64)
+    fwd_d, fwd_i = O.knn_sklearn(s64[rows], t64, c, n_jobs=-1)
+    touched = np.unique(fwd_i)
+    want_rev_d, want_rev_i = O.knn_sklearn(t64[touched], s64, c, n_jobs=-1)
+    O.assert_neighbors_match(rev_dist[touched].cpu().numpy(), rev_ind[touched].cpu().numpy(),
+                             want_rev_d, want_rev_i, RTOL, ATOL, what="c4 reverse (column side)")
+    r_train = np.zeros(m)
+    r_train[touched] = want_rev_d.mean(axis=1)
+    want = 2 * fwd_d - fwd_d.mean(axis=1, keepdims=True) - r_train[fwd_i]
+    want_d, want_i = O.sort_topk(want, fwd_i, k)
+    O.assert_neighbors_match(dist[rows].cpu().numpy(), ind[rows].cpu().numpy(), want_d, want_i,
+                             RTOL, ATOL, what="c4 forward + CSLS")
+    scores = hubness_score(ind, m, k=k, store_k_occurrence=True)
+    assert int(scores["k_occurrence"].sum()) == n * k          # checksum of the histogram
