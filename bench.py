@@ -62,6 +62,8 @@ def parse_args():
     ap.add_argument("--precision", default="auto", choices=["auto", "tf32x3", "screen"],
                     help="candidate search: 3xTF32 keys, or 1xTF32 screen + float64 proof + 3xTF32 "
                          "re-search of unproven rows (same results)")
+    ap.add_argument("--data", default="gaussian", choices=["gaussian", "hubby"],
+                    help="synthetic distribution (see synth)")
     ap.add_argument("--no-hub-scores", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -76,17 +78,28 @@ def workload(args):
             w[key] = getattr(args, key)
     if args.hubness is not None:
         w["hubness"] = None if args.hubness.lower() in ("none", "no") else args.hubness
-    w["name"] = (f"{args.workload}: {w['n']}x{w['m']} d={w['d']} fp32 gaussian, exact kNN "
+    w["name"] = (f"{args.workload}: {w['n']}x{w['m']} d={w['d']} fp32 {args.data}, exact kNN "
                  f"c={w['c']} + {w['hubness']} k={w['k']}")
     return w
 
 
-def synth(n, d, seed, device):
+def synth(n, d, seed, device, data="gaussian"):
+    """Synthetic embeddings: i.i.d. standard normal (almost no near ties, mild hubness), or
+    "hubby": a unit-normalised Gaussian mixture of 300 clusters shared by source and target
+    (relative noise 0.25: neighbour gaps around the TF32 error bound, strong hubness)."""
     import torch
 
     g = torch.Generator(device=device)
     g.manual_seed(seed)
-    return torch.randn((n, d), generator=g, device=device, dtype=torch.float32)
+    if data == "gaussian":
+        return torch.randn((n, d), generator=g, device=device, dtype=torch.float32)
+    gc = torch.Generator(device=device)
+    gc.manual_seed(12345)                                  # same centres for both sides
+    centres = torch.randn((300, d), generator=gc, device=device, dtype=torch.float32)
+    x = torch.randn((n, d), generator=g, device=device, dtype=torch.float32)
+    assign = torch.randint(0, 300, (n,), generator=g, device=device)
+    x.mul_(0.25).add_(centres[assign])
+    return torch.nn.functional.normalize(x, dim=1)
 
 
 # ---------------------------------------------------------------------------
@@ -188,9 +201,18 @@ def run_reference(args, w):
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0))
-    rng = np.random.default_rng(0)
-    source = rng.standard_normal((w["n"], w["d"]), dtype=np.float32)
-    target = np.random.default_rng(1).standard_normal((w["m"], w["d"]), dtype=np.float32)
+
+    def synth_np(n, seed):
+        rng = np.random.default_rng(seed)
+        x = rng.standard_normal((n, w["d"]), dtype=np.float32)
+        if args.data == "hubby":          # same distribution as synth() (other random streams)
+            centres = np.random.default_rng(12345).standard_normal((300, w["d"]), dtype=np.float32)
+            x = 0.25 * x + centres[rng.integers(0, 300, n)]
+            x /= np.linalg.norm(x, axis=1, keepdims=True)
+        return x
+
+    source = synth_np(w["n"], 0)
+    target = synth_np(w["m"], 1)
     sample = cpu_sample_rows(w, args.cpu_sample)
     for _ in range(min(args.warmup, 1)):
         cpu_reference_step(w, min(sample, 256), source, target)
@@ -269,8 +291,8 @@ def run_b200(args, w):
             dist.barrier()
         torch.cuda.synchronize()
 
-    source = synth(w["n"], w["d"], 0, device)
-    target = synth(w["m"], w["d"], 1, device)
+    source = synth(w["n"], w["d"], 0, device, args.data)
+    target = synth(w["m"], w["d"], 1, device, args.data)
     hub_kwargs = HUB_KWARGS.get(w["hubness"], {})
 
     def make():

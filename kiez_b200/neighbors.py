@@ -224,6 +224,7 @@ class B200Mixin:
             raise ValueError(f"fused must be 'auto', True or False, got {fused!r}")
         self.fused = fused
         self._fused_forward = None     # forward result cached by the dual-direction pass
+        self._screen_ok = None         # verdict of the screen probe for this fit (None: not probed)
         self._prepared = {}
         self._center_vec = None
         self._input_is_numpy = False
@@ -238,6 +239,7 @@ class B200Mixin:
         self._prepared = {}
         self._center_vec = None
         self._fused_forward = None
+        self._screen_ok = None
         self._input_is_numpy = isinstance(source, np.ndarray)
         return super().fit(source, target, only_fit_target=only_fit_target)
 
@@ -367,11 +369,31 @@ class B200Mixin:
         the 3xTF32 search) and needs a full list per row to say anything."""
         if self.precision == "tf32x3" or self.impl not in ("auto", "tc"):
             return False
+        if self.precision == "auto" and self._screen_ok is False:
+            return False                 # the probe of this fit found the proof failing too often
         if q.raw.dtype != torch.float32 or y.raw.dtype != torch.float32:
             return False
         if q.dpad != y.dpad or y.n < 4 * cap or q.n < 1:
             return False
         return self._lib.lib.kb2_screen_stages(q.dpad, cap, int(dual)) > 0
+
+    # The screen pays off while the proof holds for most rows.  On data whose neighbour gaps are
+    # below the TF32 error bound (tight clusters of normalised vectors) nearly every row would be
+    # searched twice, so with precision="auto" the first rows of a fit are a PROBE: if more than
+    # SCREEN_MAX_UNVERIFIED of them fail the proof, the rest of the fit uses the 3xTF32 kernels.
+    SCREEN_MAX_UNVERIFIED = 0.25
+    SCREEN_PROBE_ROWS = 18944            # one-direction search: 2 x 128 rows for each of 74 CTA pairs
+
+    def _screen_verdict(self, unverified) -> bool:
+        """Record (once per fit) whether the screen stays on, from the `unverified` flags of the
+        probe rows; one host sync."""
+        if self.precision != "auto":
+            return True
+        if self._screen_ok is None:
+            frac = float(unverified.to(torch.float32).mean()) if unverified.numel() else 0.0
+            self._screen_ok = frac <= self.SCREEN_MAX_UNVERIFIED
+            self.search_stats["screen_probe_unverified"] = frac
+        return self._screen_ok
 
     def _eps_dot(self, dpad: int) -> float:
         """Relative bound of |<hi(q), hi(y)> (fp32 accumulate) - <q, y>| / (|q| |y|): both
@@ -564,6 +586,11 @@ class B200Mixin:
                                          lib.ptr(key_rows) + 4 * (cap - 1), r_lists * cap, cap, r_lists,
                                          out=(fwd_d[lo:hi], fwd_i[lo:hi], unv_rows[lo:hi]))
                     del key_rows
+                    if lo == 0 and len(bounds) > 2 and not self._screen_verdict(unv_rows[lo:hi]):
+                        # probe failed: start over with 3xTF32 keys (_use_screen now says no)
+                        del cand_rows, col_buf, col_cnt, fwd_d, fwd_i, unv_rows, tau
+                        return self.search_both(rows, cols, k_rows, k_cols,
+                                                exclude_self_rows=exclude_self_rows)
                 else:
                     splits = lib.lib.kb2_suggest_splits(seg.n, cols.n, cap, sm)
                     cand_rows = torch.empty((seg.n, splits * cap), dtype=torch.int32, device=dev)
@@ -659,12 +686,31 @@ class B200Mixin:
         if q.n == 0 or splits is not None or not self._use_screen(q, y, cap, dual=False) \
                 or (exclude_self and y.n < k + 2):
             return self._search_tf32x3(q, y, k, exclude_self=exclude_self, splits=splits)
-        with torch.cuda.device(self.device):
-            cand, ckey, lists = self._screen_search(q, y, cap)
-            out_d, out_i, unv = self._refine_checked(q, y, cand, k, exclude_self,
-                                                     lib.ptr(ckey) + 4 * (cap - 1), lists * cap, cap,
-                                                     lists)
-            self.search_stats["screen_rows"] += q.n
+        dev = self.device
+        with torch.cuda.device(dev):
+            out_d = torch.empty((q.n, k), dtype=torch.float64, device=dev)
+            out_i = torch.empty((q.n, k), dtype=torch.int64, device=dev)
+            unv = torch.empty((q.n,), dtype=torch.int32, device=dev)
+            parts = [(0, q.n)]
+            if self.precision == "auto" and self._screen_ok is None and \
+                    q.n >= 4 * self.SCREEN_PROBE_ROWS:
+                parts = [(0, self.SCREEN_PROBE_ROWS), (self.SCREEN_PROBE_ROWS, q.n)]
+            for lo, hi in parts:
+                part = q if (lo, hi) == (0, q.n) else q.rows(lo, hi)
+                if self._screen_ok is False:          # the probe said no: 3xTF32 for the rest
+                    d_p, i_p = self._search_tf32x3(part, y, k, exclude_self=exclude_self)
+                    out_d[lo:hi] = d_p
+                    out_i[lo:hi] = i_p
+                    unv[lo:hi] = 0
+                    continue
+                cand, ckey, lists = self._screen_search(part, y, cap)
+                self._refine_checked(part, y, cand, k, exclude_self, lib.ptr(ckey) + 4 * (cap - 1),
+                                     lists * cap, cap, lists,
+                                     out=(out_d[lo:hi], out_i[lo:hi], unv[lo:hi]))
+                self.search_stats["screen_rows"] += hi - lo
+                del cand, ckey
+                if len(parts) > 1 and lo == 0:
+                    self._screen_verdict(unv[lo:hi])
             self._research(q, y, torch.nonzero(unv).flatten(), k, exclude_self, out_d, out_i)
         return out_d, out_i
 

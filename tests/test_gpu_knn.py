@@ -314,3 +314,69 @@ def test_screen_not_taken_for_float64_or_wide_rows():
     want_d, want_i = O.knn_brute(q.astype(np.float64), y.astype(np.float64), 5, "euclidean")
     O.assert_neighbors_match(dist.cpu().numpy(), ind.cpu().numpy(), want_d, want_i, RTOL, ATOL,
                              what="wide rows")
+
+
+def _tight_clusters(n, d, seed, noise=0.02):
+    """Unit vectors in 8 very tight clusters: neighbour gaps far below the TF32 error bound."""
+    rng = np.random.default_rng(seed)
+    cent = np.random.default_rng(99).standard_normal((8, d))
+    x = cent[rng.integers(0, 8, n)] + noise * rng.standard_normal((n, d))
+    return (x / np.linalg.norm(x, axis=1, keepdims=True)).astype(np.float32)
+
+
+@pytest.mark.parametrize("tight", [False, True])
+def test_screen_probe_one_direction(tight):
+    """precision="auto": the leading rows of the first search of a fit are a probe; where the
+    proof fails for most of them (tight clusters) the rest runs on 3xTF32 keys.  Exact either way."""
+    from kiez_b200 import B200
+
+    nq, ny, d, k = 3000, 4000, 64, 10
+    if tight:
+        q, y = _tight_clusters(nq, d, 1), _tight_clusters(ny, d, 2)
+    else:
+        q, y = _data(nq, ny, d, seed=5)
+    algo = B200(n_candidates=k, fused=False)
+    algo.SCREEN_PROBE_ROWS = 512
+    algo.fit(q, y)
+    dist, ind = algo.kneighbors(k=k)
+    assert algo._screen_ok is (not tight), algo.search_stats
+    if tight:
+        assert algo.search_stats["screen_probe_unverified"] > 0.25
+        assert algo.search_stats["screen_rows"] == 512          # only the probe was screened
+    else:
+        assert algo.search_stats["screen_rows"] == nq
+    want_d, want_i = O.knn_brute(q.astype(np.float64), y.astype(np.float64), k, "euclidean")
+    O.assert_neighbors_match(dist.cpu().numpy(), ind.cpu().numpy(), want_d, want_i, RTOL, ATOL,
+                             what=f"probe tight={tight}")
+    # the verdict holds for the rest of the fit, a new fit probes again
+    dist2, ind2 = algo.kneighbors(k=k, query=y, s_to_t=False)
+    assert algo.search_stats["screen_rows"] == (512 if tight else nq + ny)
+    want_d, want_i = O.knn_brute(y.astype(np.float64), q.astype(np.float64), k, "euclidean")
+    O.assert_neighbors_match(dist2.cpu().numpy(), ind2.cpu().numpy(), want_d, want_i, RTOL, ATOL,
+                             what=f"probe reverse tight={tight}")
+    algo.fit(q, y)
+    assert algo._screen_ok is None
+
+
+@pytest.mark.parametrize("tight", [False, True])
+def test_screen_probe_dual_direction(tight):
+    """Dual-direction pass: the first row segment is the probe; on failure the pass starts over
+    with the 3xTF32 kernels."""
+    from kiez_b200 import B200
+
+    nq, ny, d, c = 5000, 1500, 64, 10
+    if tight:
+        q, y = _tight_clusters(nq, d, 3), _tight_clusters(ny, d, 4)
+    else:
+        q, y = _data(nq, ny, d, seed=6)
+    algo = B200(n_candidates=c, fused=True)
+    algo.FUSED_SEGMENT_MIN_ROWS = 256
+    qp, yp = algo._prepare(q, cache=False), algo._prepare(y, cache=False)
+    (fd, fi), (rd, ri) = algo.search_both(qp, yp, c, c)
+    assert algo._screen_ok is (not tight), algo.search_stats
+    assert algo.search_stats["screen_rows"] == (0 if tight else nq + ny)
+    q64, y64 = q.astype(np.float64), y.astype(np.float64)
+    want_d, want_i = O.knn_brute(q64, y64, c, "euclidean")
+    O.assert_neighbors_match(fd.cpu().numpy(), fi.cpu().numpy(), want_d, want_i, RTOL, ATOL, what="fwd")
+    want_d, want_i = O.knn_brute(y64, q64, c, "euclidean")
+    O.assert_neighbors_match(rd.cpu().numpy(), ri.cpu().numpy(), want_d, want_i, RTOL, ATOL, what="rev")
