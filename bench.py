@@ -247,6 +247,30 @@ def measured_peaks():
     return {"bf16_sustained": 1400.0, "bf16_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback"}
 
 
+def ncu_traffic(kind):
+    """DRAM bytes (read + write) of ONE launch of the dominant kernel from the committed
+    `ncu --set full` summary under profiles/ (tools/ncu_summary.py), or None."""
+    name = {"screen-dual": "r01_ncu_knn_screen_dual_final.txt",
+            "screen": "r01_ncu_knn_screen_rows.txt",
+            "tf32x3-dual": "r01_ncu_knn_fused.txt",
+            "tf32x3": "r01_ncu_knn_tc2_pair_bk32.txt"}.get(kind)
+    path = os.path.join(ROOT, "profiles", name) if name else None
+    if not path or not os.path.exists(path):
+        return None, None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    total, ms = 0.0, None
+    with open(path) as fh:
+        for line in fh:
+            parts = line.split()
+            if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                total += float(parts[1]) * unit.get(parts[2], 1.0)
+            if len(parts) >= 3 and parts[0] == "gpu__time_duration.sum" and parts[2] == "ms":
+                ms = float(parts[1])
+    if total <= 0:
+        return None, None
+    return total, f"profiles/{name}: dram read+write of the captured launch ({ms} ms under ncu)"
+
+
 def tf32_cublas_tflops(device):
     """cuBLAS TF32 GEMM rate measured live (MEASURED_PEAKS.json has no TF32 entry)."""
     import torch
@@ -393,7 +417,9 @@ def run_b200(args, w):
         "bound": "tensor",
         "kernel": kernel_names[kind],
         "achieved": achieved, "peak": tf32_peak / mmas, "unit": "TFLOP/s",
-        "frac": achieved / (tf32_peak / mmas), "traffic": None,
+        "frac": achieved / (tf32_peak / mmas), "traffic": ncu_traffic(kind)[0],
+        "traffic_unit": "bytes per captured launch (tensor-bound kernel: DRAM is ~1 % utilised)",
+        "traffic_source": ncu_traffic(kind)[1],
         "issued_tf32_tflops": mmas * achieved, "tf32_peak": tf32_peak,
         "peak_source": f"{peaks['source']} bf16_tflops_sustained / 2 (TF32 rate)" +
                        (" / 3 (3xTF32 issues 3 MMAs per algorithmic MAC)" if mmas == 3.0 else ""),

@@ -1,0 +1,32 @@
+"""not gpu: the evidence tooling runs on the committed artefacts (launch-list summary,
+roofline.traffic lookup), so a broken tool is noticed before GPU time is spent."""
+import importlib.util
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_launch_summary_on_committed_csv():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "launch_summary.py"),
+                          os.path.join(ROOT, "profiles", "r01_launches_c4_final.csv"), "cmd"],
+                         capture_output=True, text=True, check=True).stdout
+    lines = [ln for ln in out.splitlines() if "knn_screen_kernel<1>" in ln]
+    assert len(lines) == 1
+    share = float(lines[0].split()[-1].rstrip("%"))
+    assert 85.0 < share < 95.0          # the dominant kernel's share of the step
+    assert "cutlass" in out and out.count("%") > 10
+
+
+def test_bench_traffic_lookup_reads_the_ncu_summary():
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    traffic, source = bench.ncu_traffic("screen-dual")
+    assert traffic is not None and 1e10 < traffic < 1e11
+    assert "r01_ncu_knn_screen_dual_final.txt" in source
+    assert bench.ncu_traffic("no-such-kind") == (None, None)
+    # the CPU-leg sample stays bounded (about 10-30 s of work at C4)
+    w = dict(bench.WORKLOADS["c4"])
+    assert 1024 <= bench.cpu_sample_rows(w, 0) <= 8192
