@@ -111,6 +111,51 @@ def main():
     rec["toy_k_skewness"] = np.float64(0.9128709291752769)
     np.savez_compressed(os.path.join(GOLDEN, "hubness_score.npz"), **rec)
     print("wrote hubness_score", len(rec), "arrays")
+    openea_golden()
+
+
+def write_openea_dir(root, seed=3, n_rows=60, d=7):
+    """A small OpenEA-layout directory (kiez/io/data_loading.py:35-40) with the awkward cases:
+    interleaved rows of the two graphs, rows of no graph, an id past the end of the matrix, one
+    entity listed for two rows, links for a subset of the entities."""
+    rng = np.random.default_rng(seed)
+    emb_dir, kg_dir = os.path.join(root, "emb"), os.path.join(root, "kg")
+    os.makedirs(emb_dir, exist_ok=True)
+    os.makedirs(kg_dir, exist_ok=True)
+    emb = rng.standard_normal((n_rows, d)).astype(np.float32)
+    np.save(os.path.join(emb_dir, "ent_embeds.npy"), emb)
+    perm = rng.permutation(n_rows)
+    rows1, rows2 = perm[:25], perm[25:52]            # 8 rows belong to neither graph
+    with open(os.path.join(emb_dir, "kg1_ent_ids"), "w") as fh:
+        for r in rows1:
+            fh.write(f"http://kg1/e{r}\t{r}\n")
+        fh.write(f"http://kg1/beyond\t{n_rows + 5}\n")           # no such row
+        fh.write(f"http://kg1/e{rows1[0]}\t{perm[59]}\n")         # same entity, second row
+    with open(os.path.join(emb_dir, "kg2_ent_ids"), "w") as fh:
+        for r in rows2:
+            fh.write(f"http://kg2/e{r}\t{r}\n")
+    with open(os.path.join(kg_dir, "ent_links"), "w") as fh:
+        for a, b in zip(rows1[1:21], rows2[:20]):
+            fh.write(f"http://kg1/e{a}\thttp://kg2/e{b}\n")
+    return emb_dir, kg_dir
+
+
+def openea_golden():
+    """tests/golden/openea_small/: the directory above + what the reference's own
+    kiez.io.data_loading.from_openea returns for it."""
+    import json
+
+    from kiez.io.data_loading import from_openea
+
+    root = os.path.join(GOLDEN, "openea_small")
+    emb_dir, kg_dir = write_openea_dir(root)
+    emb1, emb2, ids1, ids2, links = from_openea(emb_dir, kg_dir)
+    np.savez_compressed(os.path.join(root, "expected.npz"), emb1=emb1, emb2=emb2)
+    with open(os.path.join(root, "expected.json"), "w") as fh:
+        json.dump({"kg1_ids": ids1, "kg2_ids": ids2,
+                   "ent_links": {str(a): int(b) for a, b in links.items()}}, fh, indent=0,
+                  sort_keys=True)
+    print("wrote openea_small", emb1.shape, emb2.shape, len(links), "links")
 
 
 if __name__ == "__main__":
