@@ -58,7 +58,7 @@ def _select_rows(n_rows: int, kg_ids: Dict[int, str]):
         rows = np.sort(rows[(rows >= 0) & (rows < n_rows)])
     else:
         rows = np.empty((0,), dtype=np.int64)
-    new_ids = {kg_ids[int(r)]: i for i, r in enumerate(rows)}
+    new_ids = {kg_ids[r]: i for i, r in enumerate(rows.tolist())}   # tolist(): plain ints
     return rows, new_ids
 
 
@@ -68,7 +68,12 @@ def _split_emb(emb, kg_ids: Dict[int, str]):
     rows, new_ids = _select_rows(len(emb), kg_ids)
     if rows.size == 0:
         return np.array([]), new_ids
-    return np.asarray(emb)[rows], new_ids
+    emb = np.asarray(emb)
+    if torch is not None and emb.ndim == 2 and emb.dtype in (np.float16, np.float32, np.float64) \
+            and emb.flags.c_contiguous and emb.flags.writeable:
+        # multi-threaded row gather (numpy's fancy indexing copies 1 KB rows on one core)
+        return torch.from_numpy(emb).index_select(0, torch.from_numpy(rows)).numpy(), new_ids
+    return emb[rows], new_ids
 
 
 def _read_openea_files(emb_dir_path, kg_path):
