@@ -26,6 +26,33 @@ def shard_bounds(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def upload_sharded(data, device, group=None) -> torch.Tensor:
+    """A host matrix every rank holds (numpy or CPU tensor, fp32 / fp64 kept, anything else ->
+    fp32) -> the full matrix on `device`, moving only 1/world of it over this rank's
+    host-to-device link: rank r uploads rows [r * per, (r + 1) * per), per = ceil(n / world), and
+    ONE all-gather (NVLink under NCCL) completes the matrix.  Backend-agnostic: the gloo tests
+    run it with device = "cpu"."""
+    import numpy as np
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n, d = data.shape
+    per = -(-n // world)
+    lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
+    if isinstance(data, np.ndarray):
+        dtype = torch.float64 if data.dtype == np.float64 else torch.float32
+        part = torch.from_numpy(np.ascontiguousarray(
+            data[lo:hi], dtype=np.float64 if dtype == torch.float64 else np.float32))
+    else:
+        dtype = torch.float64 if data.dtype == torch.float64 else torch.float32
+        part = data[lo:hi].to(dtype).contiguous()
+    full = torch.empty((world * per, d), dtype=dtype, device=device)
+    # the last rank's slice may be short: the padding rows are never read (full[:n])
+    mine = torch.zeros((per, d), dtype=dtype, device=device)
+    mine[: hi - lo].copy_(part, non_blocking=True)
+    dist.all_gather_into_tensor(full, mine, group=group)
+    return full[:n]
+
+
 def sharded_topk(local_search: Callable[[int, int], Tuple[torch.Tensor, torch.Tensor]],
                  merge: Callable[[torch.Tensor, torch.Tensor, int, int, int],
                                  Tuple[torch.Tensor, torch.Tensor]],

@@ -307,25 +307,9 @@ class B200Mixin:
                        dtype=torch.float64 if keep64 else torch.float32).contiguous()
 
     def _upload_sharded(self, data):
-        import torch.distributed as dist
+        from .distributed import upload_sharded
 
-        world, rank = dist.get_world_size(), dist.get_rank()
-        n, d = data.shape
-        per = -(-n // world)
-        lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
-        if isinstance(data, np.ndarray):
-            dtype = torch.float64 if data.dtype == np.float64 else torch.float32
-            part = torch.from_numpy(np.ascontiguousarray(
-                data[lo:hi], dtype=np.float64 if dtype == torch.float64 else np.float32))
-        else:
-            dtype = torch.float64 if data.dtype == torch.float64 else torch.float32
-            part = data[lo:hi].to(dtype).contiguous()
-        full = torch.empty((world * per, d), dtype=dtype, device=self.device)
-        mine = torch.zeros((per, d), dtype=dtype, device=self.device) if hi - lo < per else \
-            torch.empty((per, d), dtype=dtype, device=self.device)
-        mine[: hi - lo].copy_(part, non_blocking=True)
-        dist.all_gather_into_tensor(full, mine)
-        return full[:n]
+        return upload_sharded(data, self.device)
 
     def _prepare(self, data, cache: bool) -> PreparedRows:
         hit = self._prepared.get(id(data))

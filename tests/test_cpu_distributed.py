@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from kiez_b200.distributed import shard_bounds, sharded_topk
+from kiez_b200.distributed import shard_bounds, sharded_topk, upload_sharded
 from oracle import kiez_oracle as O
 
 
@@ -83,3 +83,35 @@ def test_sharded_topk_world2_gloo(nq, ny, k, exclude_self):
 def test_shard_bounds_cover():
     assert [shard_bounds(10, 3, r) for r in range(3)] == [(0, 4), (4, 7), (7, 10)]
     assert shard_bounds(2, 4, 3) == (2, 2)
+
+
+def _upload_worker(rank, world, port, data, as_tensor, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # every rank is given the same host matrix but may only read its own slice
+        per = -(-data.shape[0] // world)
+        mine = data.copy()
+        mine[: rank * per] = np.nan
+        mine[(rank + 1) * per:] = np.nan
+        full = upload_sharded(torch.from_numpy(mine) if as_tensor else mine, "cpu")
+        out[rank] = full.numpy().copy()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize(("n", "dtype", "as_tensor"), [
+    (101, np.float32, False), (64, np.float64, False), (7, np.float32, True), (33, np.float16, False)])
+def test_upload_sharded_world2_gloo(n, dtype, as_tensor):
+    """Each rank uploads ceil(n / world) rows, one all-gather completes the matrix (row counts
+    that do not divide by the world size; fp64 kept, other dtypes -> fp32)."""
+    data = np.random.default_rng(n).standard_normal((n, 5)).astype(dtype)
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_upload_worker, args=(world, _free_port(), data, as_tensor, out), nprocs=world,
+             join=True)
+    want = data.astype(np.float64 if dtype == np.float64 else np.float32)
+    for rank in range(world):
+        assert out[rank].dtype == want.dtype and out[rank].shape == want.shape
+        np.testing.assert_array_equal(out[rank], want)
