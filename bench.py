@@ -461,7 +461,7 @@ def run_b200(args, w):
                "timer": "host wall clock around fit+kneighbors incl. copies, max over ranks"}
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:      # reported at N=1 only
         cores = len(os.sched_getaffinity(0))
         sample = cpu_sample_rows(w, args.cpu_sample)
         src_np, tgt_np = source.cpu().numpy(), target.cpu().numpy()
