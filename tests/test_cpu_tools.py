@@ -30,3 +30,33 @@ def test_bench_traffic_lookup_reads_the_ncu_summary():
     # the CPU-leg sample stays bounded (about 10-30 s of work at C4)
     w = dict(bench.WORKLOADS["c4"])
     assert 1024 <= bench.cpu_sample_rows(w, 0) <= 8192
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) on a tiny workload:
+    exactly one JSON line on stdout with the contract's keys."""
+    import json
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                          "--workload", "custom", "--n", "600", "--m", "500", "--d", "32",
+                          "--c", "10", "--k", "5", "--steps", "1", "--warmup", "1",
+                          "--cpu-sample", "128"], capture_output=True, text=True, check=True,
+                         timeout=300).stdout
+    lines = [ln for ln in out.splitlines() if ln.strip()]
+    assert len(lines) == 1, out
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["higher_is_better"] is True
+    assert line["metric"] == "queries_per_s" and line["unit"] == "queries/s"
+    assert line["value"] > 0 and line["n_gpus"] == 1 and line["steps"] == 1
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "600x500" in line["config"]["workload"]
+
+
+def test_bench_reference_arm_other_ranks_stay_silent():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                          "--gpus", "2", "--workload", "c1"], capture_output=True, text=True,
+                         check=True, timeout=120, env=env).stdout
+    assert out.strip() == ""
