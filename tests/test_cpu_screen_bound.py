@@ -88,3 +88,33 @@ def test_tf32_rounding_emulation():
     rel = np.abs(to_tf32(np.float32(np.random.default_rng(0).standard_normal(10000))) /
                  np.float32(np.random.default_rng(0).standard_normal(10000)) - 1.0)
     assert rel.max() <= 2.0 ** -11 * (1 + 1e-6)
+
+
+@pytest.mark.parametrize("kind", ["gauss", "shifted", "clusters"])
+@pytest.mark.parametrize("d", [32, 256])
+def test_cosine_screen_key_error_is_within_the_proof_bound(kind, d):
+    """Cosine branch of the proof (refine.cu): rows are L2-normalised in fp32 before the TF32
+    rounding (prep.cu, normalize = 1), key = -2 <q^, y^>, exact key = 2 (cosine distance - 1),
+    E = 2 eps + 1e-6."""
+    rng = np.random.default_rng(3 * d + len(kind))
+    q = data(kind, 96, d, rng).astype(np.float32)
+    y = data(kind, 700, d, rng).astype(np.float32)
+
+    def prep(x):
+        n2 = (x.astype(np.float64) ** 2).sum(axis=1)
+        scale = (1.0 / np.sqrt(n2)).astype(np.float32)
+        return to_tf32((x * scale[:, None]).astype(np.float32))
+
+    dot = np.zeros((q.shape[0], y.shape[0]), dtype=np.float32)
+    qh, yh = prep(q), prep(y)
+    for k0 in range(0, d, 8):
+        dot = (dot + (qh[:, k0:k0 + 8].astype(np.float64)
+                      @ yh[:, k0:k0 + 8].T.astype(np.float64)).astype(np.float32)).astype(np.float32)
+    key = (np.float32(-2.0) * dot).astype(np.float64)
+    q64, y64 = q.astype(np.float64), y.astype(np.float64)
+    cos = (q64 @ y64.T) / np.outer(np.linalg.norm(q64, axis=1), np.linalg.norm(y64, axis=1))
+    exact_key = 2.0 * ((1.0 - cos) - 1.0)
+    E = 2.0 * eps_dot(d) * 1.000001 + 1e-6
+    ratio = (np.abs(key - exact_key) / E).max()
+    assert ratio <= 1.0, f"{kind} d={d}: cosine screen error exceeds E by {ratio:.3f}x"
+    assert ratio > 1e-3
