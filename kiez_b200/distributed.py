@@ -106,12 +106,15 @@ def sharded_knn(algo, q, index, k: int, exclude_self: bool, group=None):
     return sharded_topk(local_search, device_merge, index.n, k, group=group)
 
 
-def sharded_knn_both(algo, rows, cols, k_fwd: int, k_rev: int, exclude_self_rows: bool, group=None):
+def sharded_knn_both(algo, rows, cols, k_fwd: int, k_rev: int, exclude_self_rows: bool, group=None,
+                      merge=None):
     """Distributed dual-direction pass.  Each rank owns a contiguous shard of the COLUMNS
     (targets) and sees all rows (sources): its pass yields the row-wise lists over its shard
     (merged across ranks like `sharded_knn`) and the COMPLETE column-wise result for its own
     columns (every row was visited locally), which only needs an all-gather to be replicated.
-    Returns ((fwd_dist, fwd_ind), (rev_dist, rev_ind)), identical on every rank."""
+    Returns ((fwd_dist, fwd_ind), (rev_dist, rev_ind)), identical on every rank.
+    `merge` defaults to the GPU merge kernel (`device_merge`); the gloo tests inject numpy."""
+    merge = device_merge if merge is None else merge
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     lo, hi = shard_bounds(cols.n, world, rank)
@@ -124,7 +127,7 @@ def sharded_knn_both(algo, rows, cols, k_fwd: int, k_rev: int, exclude_self_rows
         fi = torch.full((rows.n, k_fwd), -1, dtype=torch.int64, device=dev)
         rd = torch.empty((0, k_rev), dtype=torch.float64, device=dev)
         ri = torch.empty((0, k_rev), dtype=torch.int64, device=dev)
-    fwd = sharded_topk(lambda _lo, _hi: (fd, fi), device_merge, cols.n, k_fwd, group=group)
+    fwd = sharded_topk(lambda _lo, _hi: (fd, fi), merge, cols.n, k_fwd, group=group)
     # reverse: pad every shard to the largest shard, one packed all-gather, trim
     per = -(-cols.n // world)
     packed = torch.zeros(2 * per * k_rev, dtype=torch.int64, device=dev)

@@ -11,7 +11,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from kiez_b200.distributed import shard_bounds, sharded_topk, upload_sharded
+from kiez_b200.distributed import (shard_bounds, sharded_knn_both, sharded_topk,
+                                   upload_sharded)
 from oracle import kiez_oracle as O
 
 
@@ -115,3 +116,73 @@ def test_upload_sharded_world2_gloo(n, dtype, as_tensor):
     for rank in range(world):
         assert out[rank].dtype == want.dtype and out[rank].shape == want.shape
         np.testing.assert_array_equal(out[rank], want)
+
+
+class _Rows:
+    """Stand-in for PreparedRows on CPU: a row range of a host matrix with its global base."""
+
+    def __init__(self, x, base=0):
+        self.x, self.base, self.n = x, base, x.shape[0]
+
+    def rows(self, lo, hi):
+        return _Rows(self.x[lo:hi], self.base + lo)
+
+
+class _OracleAlgo:
+    """What sharded_knn_both needs from B200: `device` and `search_both` (oracle arithmetic,
+    ids global through the bases, like the CUDA path)."""
+
+    device = torch.device("cpu")
+
+    def search_both(self, rows, cols, k_rows, k_cols, exclude_self_rows=False):
+        d_cols = O._pairwise(rows.x, cols.x, "euclidean")
+        d = d_cols.copy()
+        if exclude_self_rows:      # row side only (kiez's forward pass): global column id == row id
+            r = np.arange(rows.n)
+            c = r + rows.base - cols.base
+            ok = (c >= 0) & (c < cols.n)
+            d[r[ok], c[ok]] = np.inf
+        def top(mat, k, base):
+            kk = min(k, mat.shape[1])
+            order = np.argsort(mat, axis=1, kind="stable")[:, :kk]
+            dd = np.full((mat.shape[0], k), np.inf)
+            ii = np.full((mat.shape[0], k), -1, dtype=np.int64)
+            dd[:, :kk] = np.take_along_axis(mat, order, 1)
+            ii[:, :kk] = order + base
+            ii[np.isinf(dd)] = -1
+            return torch.from_numpy(dd), torch.from_numpy(ii)
+        return top(d, k_rows, cols.base), top(d_cols.T.copy(), k_cols, rows.base)
+
+
+def _both_worker(rank, world, port, x, y, k, single, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        fwd, rev = sharded_knn_both(_OracleAlgo(), _Rows(x), _Rows(y), k, k, single,
+                                    merge=_numpy_merge)
+        out[rank] = tuple(t.numpy() for t in (*fwd, *rev))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize(("nx", "ny", "k", "single"), [(40, 31, 4, False), (33, 33, 5, True),
+                                                        (9, 3, 2, False)])
+def test_sharded_knn_both_world2_gloo(nx, ny, k, single):
+    """Dual-direction pass over column shards: row-wise lists merged across ranks, column-wise
+    results complete per shard and only all-gathered (uneven shards are padded and trimmed)."""
+    rng = np.random.default_rng(nx * ny)
+    x = rng.standard_normal((nx, 6))
+    y = x.copy() if single else rng.standard_normal((ny, 6))
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_both_worker, args=(world, _free_port(), x, y, k, single, out), nprocs=world, join=True)
+    k_fwd = min(k, ny - (1 if single else 0))
+    want_fd, want_fi = O.knn_brute(x, y, k_fwd, exclude_self=single)
+    want_rd, want_ri = O.knn_brute(y, x, min(k, nx))
+    for rank in range(world):
+        fd, fi, rd, ri = out[rank]
+        O.assert_neighbors_match(fd[:, :k_fwd], fi[:, :k_fwd], want_fd, want_fi, 1e-12, 1e-12,
+                                 what=f"fwd rank{rank}")
+        O.assert_neighbors_match(rd[:, :min(k, nx)], ri[:, :min(k, nx)], want_rd, want_ri, 1e-12,
+                                 1e-12, what=f"rev rank{rank}")
