@@ -102,9 +102,14 @@ class HubnessReduction(ABC):
 
     @staticmethod
     def _sort(hubness_reduced_query_dist, query_ind, n_neighbors: int):
-        """Top-k of the rescaled candidates, ascending (base.py:72-87) -> kb2_topk_rows."""
+        """Top-k of the rescaled candidates, ascending (base.py:72-87) -> kb2_topk_rows.
+        Like the reference, the result mirrors the input container: numpy in -> numpy out,
+        torch in -> torch out on the input's device (CUDA tensors stay on the device, which is
+        what the pipeline passes)."""
         lib = _lib()
         dist, ind = hubness_reduced_query_dist, query_ind
+        was_numpy = isinstance(dist, np.ndarray)
+        back_to = dist.device if torch.is_tensor(dist) and not dist.is_cuda else None
         dev = dist.device if torch.is_tensor(dist) and dist.is_cuda else torch.device(
             "cuda", torch.cuda.current_device())
         d = _as_device(dist, dev, torch.float64)
@@ -117,10 +122,16 @@ class HubnessReduction(ABC):
             if n:
                 lib.call("kb2_topk_rows", lib.ptr(d), lib.ptr(i), n, c, 1, 0, k, lib.ptr(od),
                          lib.ptr(oi), lib.stream_ptr())
+        if was_numpy:
+            return od.cpu().numpy(), oi.cpu().numpy()
+        if back_to is not None:
+            return od.to(back_to), oi.to(back_to)
         return od, oi
 
     def _finish(self, dist, ind):
         """Mirror the caller's container type: numpy in -> numpy out (like Faiss+numpy)."""
+        if isinstance(dist, np.ndarray):          # a user-defined transform that stayed on the host
+            return dist, ind
         if getattr(self.nn_algo, "_input_is_numpy", False):
             # (pinned staging buffers were tried: the first-call cudaHostAlloc costs more than the
             # pageable copy of an (n, k) result saves)

@@ -249,3 +249,28 @@ def test_full_size_c4_sampled_parity():
                              RTOL, ATOL, what="c4 forward + CSLS")
     scores = hubness_score(ind, m, k=k, store_k_occurrence=True)
     assert int(scores["k_occurrence"].sum()) == n * k          # checksum of the histogram
+
+
+def test_sort_mirrors_the_input_container():
+    """HubnessReduction._sort (base.py:72-87; the reference's tests/hubness_reduction/
+    test_hubness_base.py): numpy in -> numpy out, torch in -> torch out on the input's device,
+    same values either way, equal to the oracle's top-k."""
+    from kiez_b200 import HubnessReduction
+
+    rng = np.random.default_rng(seed=42)
+    dist = rng.random((100, 10))
+    ind = rng.integers(low=0, high=200, size=(100, 10))
+    np_dist, np_ind = HubnessReduction._sort(dist, ind, 10)
+    assert isinstance(np_dist, np.ndarray) and isinstance(np_ind, np.ndarray)
+    t_dist, t_ind = HubnessReduction._sort(torch.tensor(dist), torch.tensor(ind), 10)
+    assert isinstance(t_dist, torch.Tensor) and isinstance(t_ind, torch.Tensor)
+    assert not t_dist.is_cuda and not t_ind.is_cuda
+    c_dist, c_ind = HubnessReduction._sort(torch.tensor(dist).cuda(), torch.tensor(ind).cuda(), 4)
+    assert c_dist.is_cuda and c_dist.shape == (100, 4)
+    np.testing.assert_array_equal(t_dist.numpy(), np_dist)
+    np.testing.assert_array_equal(t_ind.numpy(), np_ind)
+    want_d, want_i = O.sort_topk(dist, ind, 10)
+    np.testing.assert_array_equal(np_dist, want_d)
+    np.testing.assert_array_equal(np_ind, want_i)
+    np.testing.assert_array_equal(c_dist.cpu().numpy(), want_d[:, :4])
+    np.testing.assert_array_equal(c_ind.cpu().numpy(), want_i[:, :4])
