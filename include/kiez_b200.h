@@ -47,7 +47,9 @@ extern "C" {
 int kb2_version(void);
 const char *kb2_last_error(void);
 
-/* Widest candidate list (per query row, per split) the search kernels support. */
+/* Sizing helpers of the kNN stage (no counterpart in the reference: scikit-learn sizes its own
+ * chunks behind sklearn_nearest_neighbors.py:96-101).
+ * Widest candidate list (per query row, per split) the search kernels support. */
 int kb2_max_candidates(void);
 /* Padded feature count the prepared operands use for a raw feature count d. */
 int kb2_padded_dim(int d);
@@ -107,14 +109,17 @@ int kb2_knn_fused(const float *x_hi, const float *x_lo, const float *x_key, int6
                   int dpad, int cap, int splits, const float *tau_col, uint32_t *col_cnt,
                   uint64_t *col_buf, int col_cap, int64_t row_id_base, int32_t *cand_idx,
                   void *stream);
-/* Per column: the cap emitted rows with the smallest column keys -> cand_idx [ny][cap]
+/* Column side of the dual-direction pass = candidates of kiez's reverse kNN
+ * (hubness_reduction/base.py:37-42 -> neighbor_algorithm_base.py:116-136).
+ * Per column: the cap emitted rows with the smallest column keys -> cand_idx [ny][cap]
  * (-1 padded), overflow[col] = 1 if more than col_cap rows were emitted.  Optional (both or
  * neither): tau_col = the thresholds the pass ran with, col_tau [ny] out = a lower bound of
  * the column key of every row that was NOT kept (input of kb2_refine_topk_checked). */
 int kb2_col_select(const uint64_t *col_buf, const uint32_t *col_cnt, int64_t ny, int col_cap,
                    int cap, int32_t *cand_idx, int32_t *overflow, const float *tau_col,
                    float *col_tau, void *stream);
-/* Between two row segments of a dual-direction pass: per column with >= cap emitted rows, the
+/* Between two row segments of a dual-direction pass (same stage of the reverse kNN,
+ * hubness_reduction/base.py:37-42): per column with >= cap emitted rows, the
  * best cap entries move to the head of its buffer, col_cnt = cap and tau_col = the cap-th best
  * key so far (thresholds only tighten, so the bound kb2_col_select reports stays valid).  A
  * column with more than col_cap emitted rows keeps a sticky overflow count. */
@@ -122,8 +127,10 @@ int kb2_col_compact(uint64_t *col_buf, uint32_t *col_cnt, int64_t ny, int col_ca
                     float *tau_col, void *stream);
 
 /*
- * Screening candidate search (knn_screen.cu): same contract as kb2_knn_candidates /
- * kb2_knn_fused, but the keys come from ONE TF32 product (the hi halves only) -- 3x fewer
+ * Screening candidate search (knn_screen.cu): the same stage of the reference as
+ * kb2_knn_candidates / kb2_knn_fused (the ArgKmin contraction behind
+ * sklearn_nearest_neighbors.py:96-101, both directions of hubness_reduction/base.py:37-42,92-94)
+ * and the same contract, but the keys come from ONE TF32 product (the hi halves only) -- 3x fewer
  * MMAs, and the 128 x dpad query tile stays resident in shared memory.  Its candidate lists
  * are proposals: kb2_refine_topk_checked proves per row that the exact top k lies inside the
  * list and flags the rows where the proof fails, which the caller searches again with
@@ -150,7 +157,8 @@ int kb2_knn_screen(const float *q_hi, const float *q_key, int64_t nq, const floa
                    uint32_t *col_cnt, uint64_t *col_buf, int col_cap, int64_t row_id_base,
                    void *stream);
 /* max(0, max_i x[i]) -> *out (device): the largest selection term ||y - center||^2 of an
- * index, input of the completeness proof. */
+ * index, input of the completeness proof (part of the index build that replaces
+ * sklearn_nearest_neighbors.py:83-94). */
 int kb2_max_f32(const float *x, int64_t n, float *out, void *stream);
 
 /*
@@ -175,7 +183,8 @@ int kb2_refine_topk(const void *q, int64_t nq, int64_t ldq, const void *y, int64
                     double *out_dist, int64_t *out_ind, void *stream);
 
 /*
- * Exact finish + completeness proof for lists proposed by kb2_knn_screen.  Same outputs as
+ * Exact finish + completeness proof for lists proposed by kb2_knn_screen: the (dist, ind)
+ * NNAlgorithm._kneighbors must return (neighbor_algorithm_base.py:112-136).  Same outputs as
  * kb2_refine_topk; additionally unverified[row] = 0 when the float64 k-th best distance
  * proves that no index row outside the list can be among the k nearest, else 1:
  *   every non-candidate has screen key >= tau_row = min_j tau[row*tau_row_stride + j*tau_step],
@@ -212,7 +221,9 @@ int kb2_row_stats(const double *dist, int64_t n, int c, double *mean, double *sd
                   double *last, void *stream);
 
 /*
- * Rescale + final sort, one pass: out = top-k over the c candidates of
+ * Rescale + final sort, one pass (transform of csls.py:85-96, local_scaling.py:129-151,
+ * mutual_proximity.py:166-183 numpy branch, fused with HubnessReduction._sort base.py:72-87):
+ * out = top-k over the c candidates of
  *   CSLS     2 d - mean_c(d_row) - stat_a[ind]
  *   LS       1 - exp(-d^2 / (d_row[c-1] * stat_a[ind]))
  *   NICDM    d / sqrt(mean_c(d_row) * stat_a[ind])
@@ -245,7 +256,8 @@ int kb2_dsl_transform(const void *query, int64_t n, int64_t ldq, const void *tar
                       int64_t m, int64_t ldt, int d, int elem_size, const int64_t *ind, int c,
                       const double *dist_to_cent, double *raw, double *global_min,
                       void *stream);
-/* stage 2: shift by -min if negative, sqrt unless squared, top-k (k==0: unsorted). */
+/* stage 2 (dis_sim.py:171-177 + HubnessReduction._sort base.py:72-87): shift by -min if
+ * negative, sqrt unless squared, top-k (k==0: unsorted). */
 int kb2_dsl_finish_topk(const double *raw, const int64_t *ind, int64_t n, int c,
                         const double *global_min, int squared, int k, double *out_dist,
                         int64_t *out_ind, void *stream);
