@@ -49,11 +49,11 @@ const char *kb2_last_error(void);
 
 /* Sizing helpers of the kNN stage (no counterpart in the reference: scikit-learn sizes its own
  * chunks behind sklearn_nearest_neighbors.py:96-101).
- * Widest candidate list (per query row, per split) the search kernels support. */
+ *   kb2_max_candidates: widest candidate list (per query row, per split) the search kernels support
+ *   kb2_padded_dim:     padded feature count the prepared operands use for a raw feature count d
+ *   kb2_suggest_splits: number of index splits for nq queries (fills the SMs when nq is small) */
 int kb2_max_candidates(void);
-/* Padded feature count the prepared operands use for a raw feature count d. */
 int kb2_padded_dim(int d);
-/* Suggested number of index splits for nq queries (fills the SMs when nq is small). */
 int kb2_suggest_splits(int64_t nq, int64_t ny, int cap, int sm_count);
 
 /*

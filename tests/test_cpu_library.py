@@ -111,3 +111,17 @@ def test_integration_stub_calls_match_the_header_arity():
             elif ch == "," and depth == 0:
                 n_args += 1
         assert n_args == len(_lib.SIGNATURES[name]), name
+
+
+def test_every_entry_point_cites_the_reference():
+    """include/kiez_b200.h: the comment block in front of each prototype (group) names the
+    reference code it replaces (file.py:lines), as the boundary contract asks."""
+    text = open(HEADER).read()
+    pattern = re.compile(
+        r"(/\*(?:.|\n)*?\*/)\s*((?:(?:int|const char \*)\s*kb2_[a-z0-9_]+\([^;]*;\s*)+)")
+    seen = set()
+    for comment, protos in pattern.findall(text):
+        names = re.findall(r"kb2_[a-z0-9_]+(?=\()", protos)
+        seen.update(names)
+        assert re.search(r"[a-z_]+\.py:\d", comment), f"{names}: no reference citation"
+    assert seen >= set(_declared()) - {"kb2_version", "kb2_last_error"}
