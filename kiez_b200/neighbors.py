@@ -744,6 +744,11 @@ class B200(B200Mixin, NNAlgorithm):
     propose candidates with ONE TF32 product (3x fewer MMAs, knn_screen.cu), prove in the
     float64 finish that the proposal contains the exact top k, search the few rows where the
     proof fails again with 3xTF32 -- same results (``search_stats`` counts the fallbacks).
+    With "auto" the first rows of a fit are a probe: if the proof fails for more than
+    ``SCREEN_MAX_UNVERIFIED`` of them (data whose neighbour gaps are below the TF32 error
+    bound) the rest of the fit uses the 3xTF32 kernels; "screen" never falls back.
+    ``fused``: "auto" / True / False -- serve kiez's reverse and forward kNN from ONE
+    dual-direction pass (automatic for cap <= 32, d >= 192, n*m >= 2^32).
     ``distributed``: shard the index side over the ranks of an initialised
     torch.distributed (NCCL) group; default: on when world_size > 1.
     """
