@@ -199,3 +199,19 @@ def test_fused_col_cap_follows_the_list_length():
     assert B200Mixin._fused_col_cap(knobs, 16) == 512
     knobs.FUSED_COL_CAP = 16
     assert B200Mixin._fused_col_cap(knobs, 56) == 56
+
+
+@pytest.mark.parametrize(("mean", "std"), [(10.0, 3.0), (10.0, 12.5), (1.0, 4.0), (0.3, 0.9),
+                                           (50.0, 7.0), (2.0, 2.0), (5.0, 100.0)])
+def test_truncnorm_third_moment_matches_scipy(mean, std):
+    """The closed form behind `k_skewness_truncnorm` equals what the reference computes with
+    scipy (estimation.py:52-58: truncnorm(a, b).moment(3), b at the int64 maximum)."""
+    from scipy import stats
+
+    from kiez_b200.analysis import _truncnorm_third_moment
+
+    a = (0 - mean) / std
+    b = (np.iinfo(np.int64).max - mean) / std
+    want = stats.truncnorm(a, b).moment(3)
+    assert _truncnorm_third_moment(mean, std) == pytest.approx(want, rel=1e-9, abs=1e-12)
+    assert np.isnan(_truncnorm_third_moment(3.0, 0.0))
