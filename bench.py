@@ -64,6 +64,9 @@ def parse_args():
                          "re-search of unproven rows (same results)")
     ap.add_argument("--data", default="gaussian", choices=["gaussian", "hubby"],
                     help="synthetic distribution (see synth)")
+    ap.add_argument("--shard-grid", default=None,
+                    help="EXPERIMENTAL, N>1: RxC grid of ranks for the dual-direction pass "
+                         "(default: column shards)")
     ap.add_argument("--no-hub-scores", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -322,6 +325,8 @@ def run_b200(args, w):
     def make():
         algo = B200(n_candidates=w["c"], metric="euclidean", impl=args.search_impl,
                     distributed=world > 1, precision=args.precision,
+                    shard_grid=(tuple(int(v) for v in args.shard_grid.lower().split("x"))
+                                if args.shard_grid and world > 1 else None),
                     fused={"auto": "auto", "on": True, "off": False}[args.fused])
         return Kiez(n_candidates=w["c"], algorithm=algo, hubness=w["hubness"],
                     hubness_kwargs=dict(hub_kwargs))
@@ -481,8 +486,11 @@ def run_b200(args, w):
                        "search_impl": args.search_impl, "fused": args.fused,
                        "precision": args.precision,
                        "hub_scores": not args.no_hub_scores,
-                       "parallelism": f"index rows sharded over {world} GPU(s), NCCL all-gather + "
-                                      "merge kernel" if world > 1 else "single GPU"},
+                       "parallelism": (f"target rows sharded over {world} GPU(s)"
+                                       + (f" as a {args.shard_grid} rows x columns grid"
+                                          if args.shard_grid else "")
+                                       + ", NCCL all-gather + merge kernel") if world > 1
+                       else "single GPU"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": launches,
         }

@@ -143,3 +143,72 @@ def sharded_knn_both(algo, rows, cols, k_fwd: int, k_rev: int, exclude_self_rows
         rev_d[rlo:rhi] = g[r, 0, : rhi - rlo].view(torch.float64)
         rev_i[rlo:rhi] = g[r, 1, : rhi - rlo]
     return fwd, (rev_d, rev_i)
+
+
+def sharded_knn_both_grid(algo, rows, cols, k_fwd: int, k_rev: int, exclude_self_rows: bool,
+                          grid: Tuple[int, int], group=None, merge=None):
+    """Dual-direction pass on an R x C grid of ranks (R * C = world size): rank (r, c) =
+    divmod(rank, C) contracts row block r with column block c.  Compared with the column shards
+    of `sharded_knn_both` (= grid (1, world)) every row list sees world / R times more columns
+    (a shorter list fill phase per flop) and every rank finishes only n / R row lists; the price
+    is a second merge: row-wise lists are merged across the C column blocks of a row block,
+    column-wise lists across the R row blocks of a column block.  Two packed all-gathers, as
+    before.  EXPERIMENTAL: host logic covered by the gloo tests, not yet the default (DESIGN.md
+    round-2 list).  Returns ((fwd_dist, fwd_ind), (rev_dist, rev_ind)), identical on every rank."""
+    merge = device_merge if merge is None else merge
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n_r, n_c = grid
+    if n_r * n_c != world:
+        raise ValueError(f"grid {grid} does not match world size {world}")
+    r, c = divmod(rank, n_c)
+    per_r, per_c = -(-rows.n // n_r), -(-cols.n // n_c)
+    r0, r1 = min(rows.n, r * per_r), min(rows.n, (r + 1) * per_r)
+    c0, c1 = min(cols.n, c * per_c), min(cols.n, (c + 1) * per_c)
+    dev = algo.device
+    inf = float("inf")
+    # padded per-rank results: slots a block cannot fill hold +inf / -1
+    fd = torch.full((per_r, k_fwd), inf, dtype=torch.float64, device=dev)
+    fi = torch.full((per_r, k_fwd), -1, dtype=torch.int64, device=dev)
+    rd = torch.full((per_c, k_rev), inf, dtype=torch.float64, device=dev)
+    ri = torch.full((per_c, k_rev), -1, dtype=torch.int64, device=dev)
+    if r1 > r0 and c1 > c0:
+        kf, kr = min(k_fwd, c1 - c0), min(k_rev, r1 - r0)
+        (bfd, bfi), (brd, bri) = algo.search_both(rows.rows(r0, r1), cols.rows(c0, c1), kf, kr,
+                                                  exclude_self_rows=exclude_self_rows)
+        fd[: r1 - r0, :kf], fi[: r1 - r0, :kf] = bfd, bfi
+        rd[: c1 - c0, :kr], ri[: c1 - c0, :kr] = brd, bri
+
+    def gather(d, i):
+        n_loc, k = d.shape
+        packed = torch.empty(2 * n_loc * k, dtype=torch.int64, device=dev)
+        packed[: n_loc * k] = d.contiguous().view(torch.int64).reshape(-1)
+        packed[n_loc * k:] = i.reshape(-1)
+        gathered = torch.empty(world * packed.numel(), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(gathered, packed, group=group)
+        return gathered, packed.numel()
+
+    # row-wise: for row block b, the parts are the C consecutive ranks b * C .. b * C + C - 1
+    g, size = gather(fd, fi)
+    fwd_d = torch.empty((rows.n, k_fwd), dtype=torch.float64, device=dev)
+    fwd_i = torch.empty((rows.n, k_fwd), dtype=torch.int64, device=dev)
+    for b in range(n_r):
+        lo, hi = min(rows.n, b * per_r), min(rows.n, (b + 1) * per_r)
+        if hi <= lo:
+            continue
+        base = b * n_c * size
+        md, mi = merge(g[base:].view(torch.float64), g[base + per_r * k_fwd:], n_c, size, k_fwd, per_r)
+        fwd_d[lo:hi], fwd_i[lo:hi] = md[: hi - lo], mi[: hi - lo]
+    # column-wise: for column block b, the parts are ranks b, b + C, ..., b + (R - 1) * C
+    g, size = gather(rd, ri)
+    rev_d = torch.empty((cols.n, k_rev), dtype=torch.float64, device=dev)
+    rev_i = torch.empty((cols.n, k_rev), dtype=torch.int64, device=dev)
+    for b in range(n_c):
+        lo, hi = min(cols.n, b * per_c), min(cols.n, (b + 1) * per_c)
+        if hi <= lo:
+            continue
+        base = b * size
+        md, mi = merge(g[base:].view(torch.float64), g[base + per_c * k_rev:], n_r, n_c * size, k_rev,
+                       per_c)
+        rev_d[lo:hi], rev_i[lo:hi] = md[: hi - lo], mi[: hi - lo]
+    return (fwd_d, fwd_i), (rev_d, rev_i)

@@ -190,7 +190,7 @@ class B200Mixin:
     def __init__(self, n_candidates: int = 5, metric: str = "euclidean", p: int = 2,
                  device: Optional[Any] = None, impl: str = "auto", center: bool = True,
                  distributed: Optional[bool] = None, fused: Any = "auto",
-                 precision: str = "auto", n_jobs=None):
+                 precision: str = "auto", n_jobs=None, shard_grid: Optional[Tuple[int, int]] = None):
         if torch is None or not torch.cuda.is_available():
             raise ImportError(
                 "The B200 backend needs PyTorch with a CUDA device (sm_100a); there is no "
@@ -220,6 +220,13 @@ class B200Mixin:
             distributed = torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size() > 1
         self.distributed = bool(distributed)
+        # EXPERIMENTAL (off by default): run the dual-direction pass on an R x C grid of ranks
+        # instead of column shards (distributed.sharded_knn_both_grid); KB2_SHARD_GRID="RxC"
+        if shard_grid is None and os.environ.get("KB2_SHARD_GRID"):
+            shard_grid = tuple(int(v) for v in os.environ["KB2_SHARD_GRID"].lower().split("x"))
+        if shard_grid is not None and (len(shard_grid) != 2 or min(shard_grid) < 1):
+            raise ValueError(f"shard_grid must be (R, C) with R, C >= 1, got {shard_grid!r}")
+        self.shard_grid = tuple(shard_grid) if shard_grid is not None else None
         if fused not in ("auto", True, False):
             raise ValueError(f"fused must be 'auto', True or False, got {fused!r}")
         self.fused = fused
@@ -266,7 +273,12 @@ class B200Mixin:
             # forward pass that HubnessReduction.kneighbors will ask for next (base.py:92-94)
             single = bool(getattr(self, "source_equals_target", False))
             k_fwd = min(self.n_candidates, target_index.n - (1 if single else 0))
-            if self.distributed:
+            if self.distributed and self.shard_grid is not None:
+                from .distributed import sharded_knn_both_grid
+
+                fwd, rev = sharded_knn_both_grid(self, source_index, target_index, k_fwd, k, single,
+                                                 self.shard_grid)
+            elif self.distributed:
                 from .distributed import sharded_knn_both
 
                 fwd, rev = sharded_knn_both(self, source_index, target_index, k_fwd, k, single)

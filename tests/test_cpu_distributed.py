@@ -11,8 +11,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from kiez_b200.distributed import (shard_bounds, sharded_knn_both, sharded_topk,
-                                   upload_sharded)
+from kiez_b200.distributed import (shard_bounds, sharded_knn_both, sharded_knn_both_grid,
+                                   sharded_topk, upload_sharded)
 from oracle import kiez_oracle as O
 
 
@@ -186,3 +186,40 @@ def test_sharded_knn_both_world2_gloo(nx, ny, k, single):
                                  what=f"fwd rank{rank}")
         O.assert_neighbors_match(rd[:, :min(k, nx)], ri[:, :min(k, nx)], want_rd, want_ri, 1e-12,
                                  1e-12, what=f"rev rank{rank}")
+
+
+def _grid_worker(rank, world, port, x, y, k, single, grid, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        fwd, rev = sharded_knn_both_grid(_OracleAlgo(), _Rows(x), _Rows(y), k, k, single, grid,
+                                         merge=_numpy_merge)
+        out[rank] = tuple(t.numpy() for t in (*fwd, *rev))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize(("nx", "ny", "k", "single", "grid"), [
+    (41, 30, 4, False, (2, 2)), (37, 37, 5, True, (2, 2)), (40, 31, 4, False, (2, 1)),
+    (40, 31, 4, False, (1, 2)), (7, 5, 3, False, (2, 2))])
+def test_sharded_knn_both_grid_gloo(nx, ny, k, single, grid):
+    """R x C grid of ranks: row-wise lists merged across the column blocks of a row block,
+    column-wise lists across the row blocks of a column block; ragged blocks, self-exclusion
+    through the global bases, blocks smaller than k."""
+    rng = np.random.default_rng(nx * ny + grid[0])
+    x = rng.standard_normal((nx, 6))
+    y = x.copy() if single else rng.standard_normal((ny, 6))
+    world = grid[0] * grid[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_grid_worker, args=(world, _free_port(), x, y, k, single, grid, out), nprocs=world,
+             join=True)
+    k_fwd = min(k, ny - (1 if single else 0))
+    want_fd, want_fi = O.knn_brute(x, y, k_fwd, exclude_self=single)
+    want_rd, want_ri = O.knn_brute(y, x, min(k, nx))
+    for rank in range(world):
+        fd, fi, rd, ri = out[rank]
+        O.assert_neighbors_match(fd[:, :k_fwd], fi[:, :k_fwd], want_fd, want_fi, 1e-12, 1e-12,
+                                 what=f"grid fwd rank{rank}")
+        O.assert_neighbors_match(rd[:, :min(k, nx)], ri[:, :min(k, nx)], want_rd, want_ri, 1e-12,
+                                 1e-12, what=f"grid rev rank{rank}")
