@@ -2,6 +2,7 @@
 torch.profiler (CUPTI), and prints the idle gaps between consecutive kernels on the device.
 
     python tools/trace_step.py [--n 1000000 --m 1000000 --d 256 --c 10 --k 10] > gpurun_out/trace.txt
+    torchrun --nproc-per-node N tools/trace_step.py ...     # one report per rank on stdout
 """
 import argparse
 import os
@@ -24,7 +25,14 @@ def main():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--min-gap-us", type=float, default=200.0)
     args = ap.parse_args()
-    dev = torch.device("cuda", 0)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
     g = torch.Generator(device=dev)
     g.manual_seed(0)
     src = torch.randn((args.n, args.d), generator=g, device=dev)
@@ -32,7 +40,8 @@ def main():
     tgt = torch.randn((args.m, args.d), generator=g, device=dev)
 
     def step():
-        inst = Kiez(n_candidates=args.c, algorithm=B200(n_candidates=args.c), hubness="CSLS")
+        inst = Kiez(n_candidates=args.c, algorithm=B200(n_candidates=args.c, distributed=world > 1),
+                    hubness="CSLS")
         inst.fit(src, tgt)
         return inst.kneighbors(args.k)
 
@@ -49,7 +58,7 @@ def main():
         return
     t0, t1 = evs[0].time_range.start, max(e.time_range.end for e in evs)
     busy = sum(e.time_range.end - e.time_range.start for e in evs)
-    print(f"step span {1e-3 * (t1 - t0):.1f} ms, kernels+memops busy {1e-3 * busy:.1f} ms, "
+    print(f"rank {os.environ.get('RANK', '0')}/{world}: step span {1e-3 * (t1 - t0):.1f} ms, kernels+memops busy {1e-3 * busy:.1f} ms, "
           f"idle {1e-3 * (t1 - t0 - busy):.1f} ms, {len(evs)} device activities")
     print(f"gaps >= {args.min_gap_us:.0f} us (after -> before):")
     end = evs[0].time_range.end
@@ -63,6 +72,8 @@ def main():
     print("largest device activities:")
     for e in sorted(evs, key=lambda e: e.time_range.start - e.time_range.end)[:12]:
         print(f"  {1e-3 * (e.time_range.end - e.time_range.start):8.2f} ms  {e.name[:90]}")
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
