@@ -71,6 +71,14 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="rows per direction for the CPU leg")
+    ap.add_argument("--cpu-kind", default="auto", choices=["auto", "port"],
+                    help="CPU legs: the unmodified reference from baseline/_ref when present "
+                         "(auto), or the oracle port")
+    ap.add_argument("--parity-rows", type=int, default=1024,
+                    help="rows per direction checked against the oracle outside the timed region")
+    ap.add_argument("--no-variants", action="store_true",
+                    help="skip the second data distribution (data_variants)")
+    ap.add_argument("--e2e-steps", type=int, default=5)
     return ap.parse_args()
 
 
@@ -84,6 +92,17 @@ def workload(args):
     w["name"] = (f"{args.workload}: {w['n']}x{w['m']} d={w['d']} fp32 {args.data}, exact kNN "
                  f"c={w['c']} + {w['hubness']} k={w['k']}")
     return w
+
+
+def make_config(args, w, world):
+    """The `config` object of the JSON line -- the same for both arms, so that the driver can
+    pair the lines."""
+    return {"workload": w["name"], "l2": "inputs (>=1 GB) exceed the 126 MB L2",
+            "search_impl": args.search_impl, "fused": args.fused, "precision": args.precision,
+            "hub_scores": not args.no_hub_scores,
+            "parallelism": (f"rows sharded over {world} GPU(s)"
+                            + (f" as a {args.shard_grid} rows x columns grid" if args.shard_grid else "")
+                            + ", NCCL exchange + merge kernel") if world > 1 else "single GPU"}
 
 
 def synth(n, d, seed, device, data="gaussian"):
@@ -196,14 +215,42 @@ def cpu_sample_rows(w, requested):
     return int(max(64, min(rows, w["n"], w["m"], 8192)))
 
 
+def reference_kiez_step(w, sample, source, target):
+    """One bounded step of the UNMODIFIED reference (baseline/_ref, loaded through the import
+    shims of oracle/ref_shim.py): kiez.Kiez(algorithm=SklearnNN(brute, n_jobs=-1), hubness=...)
+    .fit(source[:sample], target).kneighbors(k) -- kiez/kiez.py:160-223.  The reverse pass
+    searches all m targets against the `sample` source rows and the forward pass the `sample`
+    rows against all m targets: 4 m d flop per query, the per-query cost of the full problem."""
+    import warnings
+
+    from oracle import ref_shim
+
+    kiez = ref_shim.load_reference()
+    from kiez.neighbors import SklearnNN
+
+    t0 = time.perf_counter()
+    algo = SklearnNN(n_candidates=w["c"], metric="euclidean", algorithm="brute", n_jobs=-1)
+    inst = kiez.Kiez(n_candidates=w["c"], algorithm=algo, hubness=w["hubness"],
+                     hubness_kwargs=dict(HUB_KWARGS.get(w["hubness"], {})))
+    inst.fit(source[:sample], target)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        inst.kneighbors(w["k"])
+    return time.perf_counter() - t0
+
+
 def run_reference(args, w):
     """--impl reference: the reference's own CPU implementation of the path on this box's host
-    cores.  /root/reference is not present on the GPU box, so this is the oracle port, which
+    cores, all threads, on a bounded sample of the workload per step.  Runs the unmodified
+    reference from baseline/_ref (tools/vendor_reference.sh; /root/reference does not exist on
+    the GPU box) when it is there and its hubness class has a CPU path that finishes (the
+    reference's DisSimLocal / MP-empiric are per-row Python loops), else the oracle port, which
     performs the same scikit-learn call (NearestNeighbors brute, n_jobs=-1) + numpy rescale."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0))
+    from oracle import ref_shim
 
     def synth_np(n, seed):
         rng = np.random.default_rng(seed)
@@ -217,20 +264,27 @@ def run_reference(args, w):
     source = synth_np(w["n"], 0)
     target = synth_np(w["m"], 1)
     sample = cpu_sample_rows(w, args.cpu_sample)
-    for _ in range(min(args.warmup, 1)):
-        cpu_reference_step(w, min(sample, 256), source, target)
-    times = [cpu_reference_step(w, sample, source, target) for _ in range(max(1, args.steps))]
+    real = ref_shim.reference_available() and args.cpu_kind != "port"
+    step = reference_kiez_step if real else cpu_reference_step
+    for _ in range(args.warmup):            # warm-up steps on a small sample (threads, caches)
+        step(w, min(sample, 64), source, target)
+    times = [step(w, sample, source, target) for _ in range(max(1, args.steps))]
     t = sum(times) / len(times)
     value = sample / t
+    what = (f"unmodified kiez 0.5.0 from {ref_shim.REFERENCE_ROOT} (oracle/ref_shim.py): "
+            f"Kiez(SklearnNN brute n_jobs=-1, {w['hubness']}).fit(source[:{sample}], target)"
+            f".kneighbors({w['k']})") if real else \
+           (f"oracle port: {sample} source rows vs all {w['m']} targets + {sample} target rows vs "
+            f"all {w['n']} sources + rescale")
     line = {
         "impl": "reference", "metric": "queries_per_s", "value": value, "unit": "queries/s",
-        "n_gpus": args.gpus, "steps": len(times), "warmup": min(args.warmup, 1),
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["name"]},
-        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} source rows vs all {w['m']} targets + {sample} target "
-                                   f"rows vs all {w['n']} sources + rescale, extrapolated linearly"},
+        "config": make_config(args, w, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores,
+                         "kind": "reference" if real else "port",
+                         "sample": what + ", extrapolated linearly in the number of queries"},
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
@@ -298,6 +352,85 @@ def tf32_cublas_tflops(device):
         torch.backends.cuda.matmul.allow_tf32 = old
 
 
+def oracle_parity(w, inst, final, source, target, rows_wanted, world, rank):
+    """Outside the timed region: the kNN results of BOTH directions (and, for the gather-type
+    rescalers, the final hubness-reduced neighbours) of a random row sample against the
+    scikit-learn brute-force call the reference makes (oracle.knn_sklearn,
+    sklearn_nearest_neighbors.py:96-101) with the tie tolerance of the parity tests.  Every rank
+    takes part in the device side (the searches are collective at N > 1); rank 0 runs the CPU
+    side.  Rows / columns that took the 3xTF32 re-search are force-included (up to 256 each)."""
+    import torch
+
+    algo = inst.algorithm
+    n, m, c, k = w["n"], w["m"], w["c"], w["k"]
+    fwd_d, fwd_i = algo.kneighbors(k=c)
+    hub = inst.hubness
+    if hasattr(hub, "r_dist_train_") and hasattr(hub, "r_ind_train_"):
+        rev_d, rev_i = hub.r_dist_train_, hub.r_ind_train_
+    else:
+        rev_d, rev_i = algo.kneighbors(k=c, query=algo.target_, s_to_t=False)
+    if rank != 0:
+        return None
+    from oracle import kiez_oracle as O
+
+    t0 = time.perf_counter()
+    rng = np.random.default_rng(2)
+    rows = rng.choice(n, min(rows_wanted, n), replace=False)
+    cols = rng.choice(m, min(rows_wanted, m), replace=False)
+    forced = {"rows": 0, "cols": 0}
+    researched = getattr(algo, "researched", None)
+    if researched is not None:
+        extra_r = researched["rows"].cpu().numpy()[:256]
+        extra_c = researched["cols"].cpu().numpy()[:256]
+        forced = {"rows": int(len(extra_r)), "cols": int(len(extra_c))}
+        rows, cols = np.concatenate([rows, extra_r]), np.concatenate([cols, extra_c])
+    rows = np.unique(rows)
+    # float64 copies of the same fp32 values (what the tests feed the oracle); very large
+    # workloads stay fp32 on the host -- scikit-learn upcasts its chunks to float64 itself
+    big = (n + m) * w["d"] > 1.2e9
+    s_h = source.cpu().numpy() if big else source.cpu().numpy().astype(np.float64)
+    t_h = target.cpu().numpy() if big else target.cpu().numpy().astype(np.float64)
+    want_fd, want_fi = O.knn_sklearn(s_h[rows], t_h, c, n_jobs=-1)
+    r_t = torch.as_tensor(rows, device=fwd_d.device)
+    bad_f, first_f = O.count_mismatched_rows(fwd_d[r_t].cpu().numpy(), fwd_i[r_t].cpu().numpy(),
+                                             want_fd, want_fi, 1e-5, 5e-6)
+    # final result on a few rows: needs the reverse statistics of every target they touch
+    oracle_hub = ORACLE_HUB.get(w["hubness"])
+    sel = np.sort(rng.choice(len(rows), min(64, len(rows)), replace=False)) \
+        if oracle_hub in ("csls", "nicdm", "mp_gaussian") else np.zeros(0, np.int64)
+    touched = np.unique(want_fi[sel]) if len(sel) else np.zeros(0, np.int64)
+    cols = np.unique(np.concatenate([cols, touched]))
+    want_rd, want_ri = O.knn_sklearn(t_h[cols], s_h, c, n_jobs=-1)
+    c_t = torch.as_tensor(cols, device=rev_d.device)
+    bad_r, first_r = O.count_mismatched_rows(rev_d[c_t].cpu().numpy(), rev_i[c_t].cpu().numpy(),
+                                             want_rd, want_ri, 1e-5, 5e-6)
+    bad_h, first_h = 0, None
+    if len(sel):
+        fd, fi = want_fd[sel], want_fi[sel]
+        pos = np.searchsorted(cols, fi)                     # target id -> row of want_rd
+        if oracle_hub == "csls":
+            out = O.csls_transform(fd, pos, want_rd)
+        elif oracle_hub == "nicdm":
+            out = O.local_scaling_transform(fd, pos, want_rd, "nicdm")
+        else:
+            out = O.mp_gaussian_transform(fd, pos, want_rd)
+        want_d, want_i = O.sort_topk(out, fi, k)
+        got_d, got_i = (torch.as_tensor(x) for x in final)
+        f_t = torch.as_tensor(rows[sel], device=got_d.device)
+        bad_h, first_h = O.count_mismatched_rows(got_d[f_t].cpu().numpy(), got_i[f_t].cpu().numpy(),
+                                                 want_d, want_i, 1e-5, 5e-6)
+    final_rows = sel
+    return {"rows": int(len(rows)), "columns": int(len(cols)), "final_rows": int(len(final_rows)),
+            "forced_researched": forced,
+            "mismatch": int(bad_f + bad_r + bad_h),
+            "mismatch_forward": int(bad_f), "mismatch_reverse": int(bad_r),
+            "mismatch_final": int(bad_h), "first": first_f or first_r or first_h,
+            "oracle": "oracle.knn_sklearn (the reference's NearestNeighbors brute call) on "
+                      + ("fp32 host copies" if big else "float64 copies") +
+                      "; tolerance rtol 1e-5 / atol 5e-6, ids exact outside tied runs",
+            "seconds": time.perf_counter() - t0}
+
+
 def run_b200(args, w):
     import torch
     import torch.distributed as dist
@@ -318,6 +451,13 @@ def run_b200(args, w):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
     source = synth(w["n"], w["d"], 0, device, args.data)
     target = synth(w["m"], w["d"], 1, device, args.data)
     hub_kwargs = HUB_KWARGS.get(w["hubness"], {})
@@ -328,46 +468,47 @@ def run_b200(args, w):
                     shard_grid=(tuple(int(v) for v in args.shard_grid.lower().split("x"))
                                 if args.shard_grid and world > 1 else None),
                     fused={"auto": "auto", "on": True, "off": False}[args.fused])
+        algo.host_result = "rank0"          # numpy callers: only rank 0 downloads the result
         return Kiez(n_candidates=w["c"], algorithm=algo, hubness=w["hubness"],
                     hubness_kwargs=dict(hub_kwargs))
 
-    out_algo = []
+    last = {}
 
     def step(src, tgt, profile=None, collect_stats=False):
         inst = make()
         inst.algorithm._profile = profile
         inst.algorithm._collect_stats = collect_stats
-        out_algo[:] = [inst.algorithm]
         inst.fit(src, tgt)
         dist_, ind_ = inst.kneighbors(w["k"])
         if not args.no_hub_scores:
             scores = hubness_score(torch.as_tensor(ind_, device=device), w["m"], k=w["k"])
         else:
             scores = None
+        last.update(inst=inst, out=(dist_, ind_), scores=scores)
         return dist_, ind_, scores
 
-    for _ in range(args.warmup):
-        step(source, target)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    profile = []
-    launches0 = _lib.launch_counter
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        out = step(source, target, profile)
-    ev1.record()
-    barrier()
-    launches = _lib.launch_counter - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([ms], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    def timed(src, tgt, warmup, steps, with_clocks):
+        for _ in range(warmup):
+            step(src, tgt)
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0 and with_clocks:
+            sampler.start()
+        profile = []
+        launches0 = _lib.launch_counter
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            step(src, tgt, profile)
+        ev1.record()
+        barrier()
+        launches = _lib.launch_counter - launches0
+        clocks = sampler.stop() if rank == 0 and with_clocks else None
+        ms = max_over_ranks(ev0.elapsed_time(ev1))
+        return ms, profile, launches, clocks
+
+    ms, profile, launches, clocks = timed(source, target, args.warmup, args.steps, True)
     ms_per_step = ms / args.steps
     value = w["n"] / (ms_per_step * 1e-3)
 
@@ -404,11 +545,18 @@ def run_b200(args, w):
     else:
         top_ms, top_n, top_flop, achieved, kind = 0.0, 0, 0.0, 0.0, "tf32x3"
     # emit / overflow statistics of the dual-direction pass need extra reductions and host
-    # syncs: gathered in one more step OUTSIDE the timed region
+    # syncs: gathered in one more step OUTSIDE the timed region; the same step feeds the parity
+    # check against the oracle
     step(source, target, collect_stats=True)
     barrier()
-    fused_stats = getattr(out_algo[0], "_fused_stats", None) if out_algo else None
-    search_stats = dict(getattr(out_algo[0], "search_stats", {})) if out_algo else {}
+    algo = last["inst"].algorithm
+    fused_stats = getattr(algo, "_fused_stats", None)
+    search_stats = dict(getattr(algo, "search_stats", {}))
+    parity = None
+    if args.parity_rows > 0:
+        parity = oracle_parity(w, last["inst"], last["out"], source, target, args.parity_rows,
+                               world, rank)
+        barrier()
     mmas = 1.0 if kind.startswith("screen") else 3.0      # MMAs issued per algorithmic MAC
     kernel_names = {
         "screen-dual": "knn_screen_kernel<dual> (1xTF32 tcgen05 cta_group::2, resident query tile, "
@@ -442,39 +590,78 @@ def run_b200(args, w):
         except Exception as exc:  # pragma: no cover
             roofline["tf32_cublas_tflops_live"] = f"failed: {exc}"
 
-    # end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timing
+    # end to end through the public API with HOST buffers, H2D + D2H inside the timing: first
+    # with PAGEABLE numpy arrays (what a kiez user has: the headline `e2e.value`), then with
+    # pinned ones.  One untimed step first (pinned staging buffers are allocated once per process).
     e2e = None
     if not args.no_e2e:
-        src_h = source.cpu().pin_memory().numpy()
-        tgt_h = target.cpu().pin_memory().numpy()
+        def e2e_run(src_h, tgt_h, n_steps):
+            step(src_h, tgt_h)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(n_steps):
+                d_, i_, _s = step(src_h, tgt_h)       # numpy in -> numpy out (D2H inside)
+            barrier()
+            return max_over_ranks((time.perf_counter() - t0) / n_steps), d_, i_
+
+        n_e2e = max(1, args.e2e_steps)
+        src_h, tgt_h = source.cpu(), target.cpu()
+        t_page, d_, i_ = e2e_run(src_h.numpy(), tgt_h.numpy(), n_e2e)
+        d2h = int(d_.nbytes + i_.nbytes) if isinstance(d_, np.ndarray) else 0
+        src_p, tgt_p = src_h.pin_memory(), tgt_h.pin_memory()
+        del src_h, tgt_h
+        t_pin, _d, _i = e2e_run(src_p.numpy(), tgt_p.numpy(), n_e2e)
+        # whole-job bytes: with N ranks every rank uploads its 1/N slice of both matrices (the
+        # rest arrives over NVLink) and rank 0 downloads the result
+        e2e = {"value": w["n"] / t_page, "unit": "queries/s",
+               "h2d_bytes_per_step": int(src_p.numel() * 4 + tgt_p.numel() * 4),
+               "d2h_bytes_per_step": d2h, "steps": n_e2e, "host_buffers": "pageable numpy",
+               "ms_per_step": 1e3 * t_page,
+               "pinned": {"value": w["n"] / t_pin, "ms_per_step": 1e3 * t_pin},
+               "fraction_of_device_value": (w["n"] / t_page) / value,
+               "timer": "host wall clock around fit+kneighbors(+hub scores) incl. copies, max over ranks"}
+        del src_p, tgt_p
+
+    # the same measurement on the other synthetic distribution (fewer steps)
+    variants = None
+    if not args.no_variants:
+        other = "hubby" if args.data == "gaussian" else "gaussian"
+        del source, target
+        src2 = synth(w["n"], w["d"], 0, device, other)
+        tgt2 = synth(w["m"], w["d"], 1, device, other)
+        ms2, prof2, _l, _c = timed(src2, tgt2, 1, min(args.steps, 3), False)
+        ms2 /= min(args.steps, 3)
+        step(src2, tgt2, collect_stats=True)
         barrier()
-        n_e2e = max(1, min(args.steps, 2))
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            d_, i_, _s = step(src_h, tgt_h)           # numpy in -> numpy out (D2H inside)
+        algo2 = last["inst"].algorithm
+        par2 = oracle_parity(w, last["inst"], last["out"], src2, tgt2, min(args.parity_rows, 256),
+                             world, rank) if args.parity_rows > 0 else None
         barrier()
-        t_e2e = (time.perf_counter() - t0) / n_e2e
-        if world > 1:
-            t = torch.tensor([t_e2e], device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            t_e2e = float(t.item())
-        # whole-job bytes: with N ranks every rank uploads its 1/N slice of both matrices
-        # (B200._upload_sharded; the rest arrives over NVLink) and downloads the full result
-        e2e = {"value": w["n"] / t_e2e, "unit": "queries/s",
-               "h2d_bytes_per_step": int(src_h.nbytes + tgt_h.nbytes),
-               "d2h_bytes_per_step": int(d_.nbytes + i_.nbytes) * world, "steps": n_e2e,
-               "timer": "host wall clock around fit+kneighbors incl. copies, max over ranks"}
+        kinds = sorted({p[5] for p in prof2})
+        variants = {other: {"value": w["n"] / (ms2 * 1e-3), "ms_per_step": ms2,
+                            "steps": min(args.steps, 3), "search_kinds": kinds,
+                            "screen": dict(algo2.search_stats), "parity_check": par2}}
+        source, target = src2, tgt2
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:      # reported at N=1 only
+        from oracle import ref_shim
+
         cores = len(os.sched_getaffinity(0))
         sample = cpu_sample_rows(w, args.cpu_sample)
-        src_np, tgt_np = source.cpu().numpy(), target.cpu().numpy()
-        cpu_reference_step(w, min(sample, 256), src_np, tgt_np)
-        t_cpu = cpu_reference_step(w, sample, src_np, tgt_np)
-        cpu = {"value": sample / t_cpu, "unit": "queries/s", "cores": cores, "kind": "port",
-               "sample": f"{sample} source rows vs all {w['m']} targets + {sample} target rows vs "
-                         f"all {w['n']} sources + rescale ({t_cpu:.1f} s), extrapolated linearly"}
+        src_np, tgt_np = source.cpu().numpy(), target.cpu().numpy()   # same shapes either way
+        real = ref_shim.reference_available() and args.cpu_kind != "port"
+        fn = reference_kiez_step if real else cpu_reference_step
+        fn(w, min(sample, 64), src_np, tgt_np)
+        t_cpu = fn(w, sample, src_np, tgt_np)
+        cpu = {"value": sample / t_cpu, "unit": "queries/s", "cores": cores,
+               "kind": "reference" if real else "port",
+               "sample": (f"unmodified kiez 0.5.0 (baseline/_ref): Kiez(SklearnNN brute, "
+                          f"{w['hubness']}).fit(source[:{sample}], target).kneighbors({w['k']})"
+                          if real else
+                          f"oracle port: {sample} source rows vs all {w['m']} targets + {sample} "
+                          f"target rows vs all {w['n']} sources + rescale")
+                         + f" ({t_cpu:.1f} s), extrapolated linearly"}
 
     if rank == 0:
         line = {
@@ -482,17 +669,9 @@ def run_b200(args, w):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "tf32" if kind.startswith("screen") else "tf32x3", "data": "synthetic",
-            "config": {"workload": w["name"], "l2": "inputs (>=1 GB) exceed the 126 MB L2",
-                       "search_impl": args.search_impl, "fused": args.fused,
-                       "precision": args.precision,
-                       "hub_scores": not args.no_hub_scores,
-                       "parallelism": (f"target rows sharded over {world} GPU(s)"
-                                       + (f" as a {args.shard_grid} rows x columns grid"
-                                          if args.shard_grid else "")
-                                       + ", NCCL all-gather + merge kernel") if world > 1
-                       else "single GPU"},
+            "config": make_config(args, w, world),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": launches,
+            "gpu_launches": launches, "parity_check": parity, "data_variants": variants,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

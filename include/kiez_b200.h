@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define KB2_VERSION 3
+#define KB2_VERSION 4
 
 /* metric codes (kiez SklearnNN metric names; minkowski/l2 are p=2 euclidean) */
 #define KB2_METRIC_EUCLIDEAN   0
@@ -160,6 +160,13 @@ int kb2_knn_screen(const float *q_hi, const float *q_key, int64_t nq, const floa
  * index, input of the completeness proof (part of the index build that replaces
  * sklearn_nearest_neighbors.py:83-94). */
 int kb2_max_f32(const float *x, int64_t n, float *out, void *stream);
+/* Rounding-error terms of the TF32 split, the other input of the completeness proof (same stage:
+ * the index build that replaces sklearn_nearest_neighbors.py:83-94).  With w the centred row,
+ * hi = rn_tf32(w) and lo = rn_tf32(w - hi) as written by kb2_prepare_rows:
+ *   err_term [n] fp32 out: an upper bound of ||w - hi||^2 (= ||lo||^2 (1 + 2^-9), rounded up)
+ *   err_max  device scalar out: its maximum over the rows. */
+int kb2_split_error_terms(const float *lo, int64_t n, int dpad, float *err_term, float *err_max,
+                          void *stream);
 
 /*
  * Exact finish -- recomputes the distance of every candidate in float64 from
@@ -189,11 +196,14 @@ int kb2_refine_topk(const void *q, int64_t nq, int64_t ldq, const void *y, int64
  * proves that no index row outside the list can be among the k nearest, else 1:
  *   every non-candidate has screen key >= tau_row = min_j tau[row*tau_row_stride + j*tau_step],
  *   j < tau_count (+inf = the list never filled: nothing was left out);
- *   |screen key - exact key| <= E(eps_dot, ||q-c||, max ||y-c||);  verified iff
+ *   |screen key - exact key| <= E = 2 (dq ym + qn (1 + 2^-11) dym + eps_acc qn ym) + 2^-21 (ym^2 + 2 qn ym)
+ *   with qn = ||q-c||, ym = max ||y-c||, dq = ||q-c - hi(q-c)||, dym = max ||y-c - hi(y-c)||
+ *   (the exact TF32 rounding errors of the operands, Cauchy-Schwarz per term);  verified iff
  *   exact key of the k-th best < tau_row - E.
  *   q_key [nq] / y_key_max (device scalar): selection terms of the queries / their maximum
  *   over the index (kb2_max_f32); ignored for cosine (unit rows).
- *   eps_dot: relative bound of the screen's dot-product error, 2^-10 (1 + 2^-9) + dpad 2^-23 + 2^-21.
+ *   q_err [nq] / y_err_max (device scalar): kb2_split_error_terms of the queries / the index.
+ *   eps_acc: bound of the fp32 accumulation error relative to qn ym (dpad 2^-22 + 2^-21).
  */
 int kb2_refine_topk_checked(const void *q, int64_t nq, int64_t ldq, const void *y, int64_t ny,
                             int64_t ldy, int d, int elem_size, const double *q_sqnorm,
@@ -202,7 +212,8 @@ int kb2_refine_topk_checked(const void *q, int64_t nq, int64_t ldq, const void *
                             int64_t self_offset, int k, double *out_dist, int64_t *out_ind,
                             const float *tau, int64_t tau_row_stride, int tau_step,
                             int tau_count, const float *q_key, const float *y_key_max,
-                            double eps_dot, int32_t *unverified, void *stream);
+                            const float *q_err, const float *y_err_max, double eps_acc,
+                            int32_t *unverified, void *stream);
 
 /*
  * Row-wise top-k of (dist, ind) pairs, ascending, ties by input position, NaN last.

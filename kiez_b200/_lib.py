@@ -40,9 +40,10 @@ SIGNATURES = {
     "kb2_knn_screen": [_p, _p, _i64, _p, _p, _i64, _int, _int, _int, _int, _p, _p, _p, _p, _p, _p,
                        _int, _i64, _p],
     "kb2_max_f32": [_p, _i64, _p, _p],
+    "kb2_split_error_terms": [_p, _i64, _int, _p, _p, _p],
     "kb2_refine_topk_checked": [_p, _i64, _i64, _p, _i64, _i64, _int, _int, _p, _p, _p, _int, _int,
-                                _i64, _int, _i64, _int, _p, _p, _p, _i64, _int, _int, _p, _p, _dbl,
-                                _p, _p],
+                                _i64, _int, _i64, _int, _p, _p, _p, _i64, _int, _int, _p, _p, _p,
+                                _p, _dbl, _p, _p],
     "kb2_refine_topk": [_p, _i64, _i64, _p, _i64, _i64, _int, _int, _p, _p, _p, _int, _int, _i64,
                         _int, _i64, _int, _p, _p, _p],
     "kb2_topk_rows": [_p, _p, _i64, _int, _int, _i64, _int, _p, _p, _p],
@@ -76,7 +77,8 @@ for _name, _args in SIGNATURES.items():
     _fn.argtypes = _args
 
 #: kernels each entry point launches (memsets not counted); bench.py reports the total
-KERNELS_PER_CALL = {"kb2_index_range": 2, "kb2_compact_ids": 3, "kb2_gini_numerator": 2}
+KERNELS_PER_CALL = {"kb2_index_range": 2, "kb2_compact_ids": 3, "kb2_gini_numerator": 2,
+                    "kb2_split_error_terms": 2}
 #: number of kiez_b200 kernels launched through `call` so far
 launch_counter = 0
 

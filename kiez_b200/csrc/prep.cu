@@ -65,7 +65,44 @@ max_f32_kernel(const float *__restrict__ x, int64_t n, unsigned int *__restrict_
     if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
 }
 
+// ||lo||^2 per row, rounded UP, and its maximum: lo = rn_tf32(delta) with delta = w - hi the exact
+// TF32 rounding error of the centred row w, so |delta_i| <= |lo_i| (1 + 2^-10) and
+// ||delta||^2 <= ||lo||^2 (1 + 2^-9); the fp64 sum is rounded to fp32 with another 2^-20 of slack.
+__global__ void __launch_bounds__(256)
+split_error_kernel(const float *__restrict__ lo, int64_t n, int dpad, float *__restrict__ err_term) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const float4 *lr = reinterpret_cast<const float4 *>(lo + row * dpad);
+    double acc = 0.0;
+    for (int j = lane; j < dpad / 4; j += 32) {
+        const float4 v = lr[j];
+        acc += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        err_term[row] = __double2float_ru(acc * (1.0 + 0x1p-9) * (1.0 + 0x1p-20));
+    }
+}
+
 }  // namespace kb2
+
+extern "C" int kb2_split_error_terms(const float *lo, int64_t n, int dpad, float *err_term,
+                                     float *err_max, void *stream) {
+    KB2_CHECK(n >= 0 && dpad > 0 && dpad % 32 == 0 && err_term && err_max,
+              "split_error_terms: bad arguments");
+    KB2_CUDA(cudaMemsetAsync(err_max, 0, sizeof(float), (cudaStream_t)stream));
+    if (n == 0) return 0;
+    const int warps = 8;
+    kb2::split_error_kernel<<<(unsigned)kb2::ceil_div64(n, warps), warps * 32, 0, (cudaStream_t)stream>>>(
+        lo, n, dpad, err_term);
+    KB2_LAUNCH_CHECK();
+    const int64_t blocks = kb2::ceil_div64(n, 256 * 8);
+    kb2::max_f32_kernel<<<(unsigned)(blocks > 1184 ? 1184 : blocks), 256, 0, (cudaStream_t)stream>>>(
+        err_term, n, reinterpret_cast<unsigned int *>(err_max));
+    KB2_LAUNCH_CHECK();
+    return 0;
+}
 
 extern "C" int kb2_max_f32(const float *x, int64_t n, float *out, void *stream) {
     KB2_CHECK(n >= 0 && out, "max_f32: bad arguments");

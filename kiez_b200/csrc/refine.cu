@@ -9,10 +9,20 @@ constexpr int REFINE_WARPS = 4;
 // Completeness proof for candidate lists that come from the 1xTF32 screen (knn_screen.cu).
 // Every index row NOT in the list has screen key >= tau (the list's cap-th best screen key;
 // the minimum over the lists when the index was searched in independent ranges), and
-//   |screen key - exact key| <= E = 2 eps_dot ||q-c|| ||y-c||_max + 2^-21 (||y-c||^2_max + 2 ||q-c|| ||y-c||_max)
-// (TF32 rounding of both operands <= 2^-11 each, fp32 accumulation, fp32 key terms), where
-//   exact key = d^2(q, y) - ||q-c||^2     (euclidean metrics, c = the centring vector)
-//             = 2 (cosine distance - 1)   (cosine: rows are normalised, norms are 1).
+// |screen key - exact key| <= E, where
+//   exact key  = d^2(q, y) - ||q-c||^2 = ||y-c||^2 - 2 <q-c, y-c>   (euclidean metrics, c = centring vector)
+//              = 2 (cosine distance - 1)                             (cosine: rows are normalised)
+//   screen key = fp32(y_key - 2 acc),  acc = tcgen05 fp32 accumulation of <hi(q), hi(y)>.
+// With w = the fp32 centred (normalised) row, hi = rn_tf32(w), delta = w - hi (known exactly at
+// prepare time: kb2_split_error_terms gives ||delta||^2 per row, rounded up, and its maximum):
+//   <w_q, w_y> - <hi_q, hi_y> = <delta_q, w_y> + <hi_q, delta_y>
+//   |.| <= ||delta_q|| ||w_y||_max + ||w_q|| (1 + 2^-11) ||delta_y||_max            (Cauchy-Schwarz per term)
+// plus eps_acc ||w_q|| ||w_y||_max for the accumulation (TF32 products are exact in fp32; dpad
+// additions of unknown order, truncation allowed: eps_acc = dpad 2^-22 + 2^-21, which also covers
+// the fp32 rounding of the centring), so
+//   E = 2 (dq ym + qn (1 + 2^-11) dym + eps_acc qn ym) + 2^-21 (ym^2 + 2 qn ym)     (last: fp32 key terms)
+// -- about 2.4x tighter than the operand-independent 2^-10 ||q|| ||y|| bound, since the RMS TF32
+// rounding error of a row is ~0.2 x 2^-10 of its norm.
 // So if the exact k-th best distance satisfies  key_k < tau - E  no outside row can belong to
 // the k nearest and the result is exact; otherwise unverified[row] = 1 and the caller
 // searches that row again with the 3xTF32 kernel.
@@ -20,9 +30,11 @@ struct CheckParams {
     const float *tau;          // first tau of row 0
     int64_t tau_row_stride;    // elements between rows
     int tau_step, tau_count;   // tau_count values per row, tau_step elements apart
-    const float *q_key;        // [nq] fp32 ||q-c||^2 (unused for cosine)
-    const float *y_key_max;    // device scalar: max ||y-c||^2 over the index (unused for cosine)
-    double eps_dot;            // bound of |screen dot - exact dot| / (||q-c|| ||y-c||)
+    const float *q_key;        // [nq] fp32 ||w_q||^2 (unused for cosine: 1)
+    const float *y_key_max;    // device scalar: max ||w_y||^2 over the index (unused for cosine)
+    const float *q_err;        // [nq] fp32 ||delta_q||^2, rounded up
+    const float *y_err_max;    // device scalar: max ||delta_y||^2 over the index
+    double eps_acc;            // accumulation bound relative to ||w_q|| ||w_y||
     int32_t *unverified;       // [nq] out
 };
 
@@ -111,15 +123,22 @@ refine_topk_kernel(const T *__restrict__ q, int64_t nq, int64_t ldq,
                 ok = true;                         // lists not full: every index row is a candidate
             } else if (!(kd < INFINITY)) {
                 ok = false;
-            } else if (metric == KB2_METRIC_COSINE) {
-                const double E = 2.0 * CP.eps_dot * 1.000001 + 1e-6;
-                ok = 2.0 * (kd - 1.0) + 1e-9 < (double)tau - E;
             } else {
-                const double d2 = (metric == KB2_METRIC_EUCLIDEAN) ? kd * kd : kd;
-                const double qn2 = (double)CP.q_key[row], ym2 = (double)*CP.y_key_max;
-                const double qn = sqrt(qn2) * 1.000001, ym = sqrt(ym2) * 1.000001;
-                const double E = 2.0 * CP.eps_dot * qn * ym + 4.76837158203125e-07 * (ym2 + 2.0 * qn * ym);
-                ok = d2 * (1.0 + 1e-12) < (double)tau - E + qn2 * (1.0 - 2.4e-7);
+                const bool cosine = metric == KB2_METRIC_COSINE;
+                const double up = 1.000001;            // slack of the fp32 norms and square roots
+                const double qn2 = cosine ? 1.0 : (double)CP.q_key[row];
+                const double ym2 = cosine ? 1.0 : (double)*CP.y_key_max;
+                const double qn = sqrt(qn2) * up, ym = sqrt(ym2) * up;
+                const double dq = sqrt((double)CP.q_err[row]) * up;
+                const double dym = sqrt((double)*CP.y_err_max) * up;
+                const double E = 2.0 * (dq * ym + qn * (1.0 + 0x1p-11) * dym + CP.eps_acc * qn * ym) +
+                                 4.76837158203125e-07 * (ym2 + 2.0 * qn * ym);
+                if (cosine) {
+                    ok = 2.0 * (kd - 1.0) + 1e-9 < (double)tau - E - 1e-6;
+                } else {
+                    const double d2 = (metric == KB2_METRIC_EUCLIDEAN) ? kd * kd : kd;
+                    ok = d2 * (1.0 + 1e-12) < (double)tau - E + qn2 * (1.0 - 2.4e-7);
+                }
             }
             CP.unverified[row] = ok ? 0 : 1;
         }
@@ -233,16 +252,19 @@ extern "C" int kb2_refine_topk_checked(const void *q, int64_t nq, int64_t ldq, c
                                        int64_t index_base, int exclude_self, int64_t self_offset,
                                        int k, double *out_dist, int64_t *out_ind, const float *tau,
                                        int64_t tau_row_stride, int tau_step, int tau_count,
-                                       const float *q_key, const float *y_key_max, double eps_dot,
+                                       const float *q_key, const float *y_key_max,
+                                       const float *q_err, const float *y_err_max, double eps_acc,
                                        int32_t *unverified, void *stream) {
     using namespace kb2;
     KB2_CHECK(tau && unverified && tau_count >= 1, "refine_topk_checked: tau and unverified are required");
     KB2_CHECK(metric == KB2_METRIC_COSINE || (q_key && y_key_max),
               "refine_topk_checked: euclidean metrics need q_key and y_key_max");
-    KB2_CHECK(eps_dot > 0.0 && eps_dot < 100.0, "refine_topk_checked: eps_dot=%g out of range", eps_dot);
+    KB2_CHECK(q_err && y_err_max, "refine_topk_checked: q_err and y_err_max (kb2_split_error_terms) are required");
+    KB2_CHECK(eps_acc > 0.0 && eps_acc < 1.0, "refine_topk_checked: eps_acc=%g out of range", eps_acc);
     CheckParams CP;
     CP.tau = tau; CP.tau_row_stride = tau_row_stride; CP.tau_step = tau_step; CP.tau_count = tau_count;
-    CP.q_key = q_key; CP.y_key_max = y_key_max; CP.eps_dot = eps_dot; CP.unverified = unverified;
+    CP.q_key = q_key; CP.y_key_max = y_key_max; CP.q_err = q_err; CP.y_err_max = y_err_max;
+    CP.eps_acc = eps_acc; CP.unverified = unverified;
     return refine_dispatch<true>(q, nq, ldq, y, ny, ldy, d, elem_size, q_sqnorm, y_sqnorm, cand_idx,
                                  ncand, metric, index_base, exclude_self, self_offset, k, out_dist,
                                  out_ind, CP, (cudaStream_t)stream);

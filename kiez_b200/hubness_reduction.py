@@ -133,6 +133,13 @@ class HubnessReduction(ABC):
         if isinstance(dist, np.ndarray):          # a user-defined transform that stayed on the host
             return dist, ind
         if getattr(self.nn_algo, "_input_is_numpy", False):
+            # distributed runs replicate the result on every rank's device; with
+            # `algorithm.host_result = "rank0"` only rank 0 pays the device-to-host copy (the
+            # other ranks keep their device tensors)
+            if getattr(self.nn_algo, "host_result", "all") == "rank0" and \
+                    getattr(self.nn_algo, "distributed", False) and \
+                    torch.distributed.get_rank() != 0:
+                return dist, ind
             # (pinned staging buffers were tried: the first-call cudaHostAlloc costs more than the
             # pageable copy of an (n, k) result saves)
             return dist.cpu().numpy(), ind.cpu().numpy()

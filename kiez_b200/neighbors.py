@@ -151,11 +151,15 @@ class PreparedRows:
     """Device-resident operands of one embedding matrix: the raw fp32 rows (exact
     finish), their 3xTF32 split and selection term (candidate search)."""
 
-    __slots__ = ("raw", "hi", "lo", "key", "sqnorm", "keymax", "n", "d", "dpad", "base", "_owner")
+    __slots__ = ("raw", "hi", "lo", "key", "sqnorm", "keymax", "err", "errmax", "n", "d", "dpad",
+                 "base", "_owner")
 
-    def __init__(self, raw, hi, lo, key, sqnorm, base=0, owner=None, keymax=None):
+    def __init__(self, raw, hi, lo, key, sqnorm, base=0, owner=None, keymax=None, err=None,
+                 errmax=None):
         self.raw, self.hi, self.lo, self.key, self.sqnorm = raw, hi, lo, key, sqnorm
         self.keymax = keymax    # device scalar >= max(key): input of the screen's completeness proof
+        # TF32 rounding error of the rows: err [n] >= ||w - hi||^2, errmax (device scalar) its maximum
+        self.err, self.errmax = err, errmax
         self.n, self.d = raw.shape
         self.dpad = hi.shape[1]
         self.base = base        # global id of row 0 (multi-GPU shards)
@@ -166,13 +170,16 @@ class PreparedRows:
         return PreparedRows(self.raw.index_select(0, idx), self.hi.index_select(0, idx),
                             self.lo.index_select(0, idx), self.key.index_select(0, idx),
                             None if self.sqnorm is None else self.sqnorm.index_select(0, idx),
-                            base=0, owner=self._owner, keymax=self.keymax)
+                            base=0, owner=self._owner, keymax=self.keymax,
+                            err=None if self.err is None else self.err.index_select(0, idx),
+                            errmax=self.errmax)
 
     def rows(self, lo, hi):
         """A contiguous row shard (views, no copy)."""
         return PreparedRows(self.raw[lo:hi], self.hi[lo:hi], self.lo[lo:hi], self.key[lo:hi],
                             None if self.sqnorm is None else self.sqnorm[lo:hi],
-                            base=self.base + lo, owner=self._owner, keymax=self.keymax)
+                            base=self.base + lo, owner=self._owner, keymax=self.keymax,
+                            err=None if self.err is None else self.err[lo:hi], errmax=self.errmax)
 
 
 def candidate_capacity(c: int) -> int:
@@ -206,6 +213,10 @@ class B200Mixin:
             raise ValueError(f"impl must be 'auto', 'tc', 'tc1' or 'simt', got {impl!r}")
         if precision not in ("auto", "tf32x3", "screen"):
             raise ValueError(f"precision must be 'auto', 'tf32x3' or 'screen', got {precision!r}")
+        if isinstance(n_candidates, (int, np.integer)) and n_candidates > _lib.lib.kb2_max_candidates():
+            raise ValueError(
+                f"B200 keeps at most {_lib.lib.kb2_max_candidates()} candidates per query "
+                f"(the lists live in shared memory), got n_candidates={n_candidates}")
         super().__init__(n_candidates=n_candidates, metric=metric, n_jobs=n_jobs)
         self.p = p
         self.impl = impl
@@ -220,6 +231,9 @@ class B200Mixin:
             distributed = torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size() > 1
         self.distributed = bool(distributed)
+        # numpy callers in distributed runs: "all" = every rank copies the (replicated) result
+        # to its host, "rank0" = only rank 0 does (the others keep device tensors)
+        self.host_result = "all"
         # EXPERIMENTAL (off by default): run the dual-direction pass on an R x C grid of ranks
         # instead of column shards (distributed.sharded_knn_both_grid); KB2_SHARD_GRID="RxC"
         if shard_grid is None and os.environ.get("KB2_SHARD_GRID"):
@@ -232,6 +246,7 @@ class B200Mixin:
         self.fused = fused
         self._fused_forward = None     # forward result cached by the dual-direction pass
         self._screen_ok = None         # verdict of the screen probe for this fit (None: not probed)
+        self._screen_boost = False     # the probe asked for longer candidate lists
         self._prepared = {}
         self._center_vec = None
         self._input_is_numpy = False
@@ -247,6 +262,7 @@ class B200Mixin:
         self._center_vec = None
         self._fused_forward = None
         self._screen_ok = None
+        self._screen_boost = False
         self._input_is_numpy = isinstance(source, np.ndarray)
         return super().fit(source, target, only_fit_target=only_fit_target)
 
@@ -353,7 +369,11 @@ class B200Mixin:
                     sqn = (raw * raw).sum(dim=1)      # exact norms of the float64 rows
             keymax = torch.empty((1,), dtype=torch.float32, device=self.device)
             lib.call("kb2_max_f32", lib.ptr(key), n, lib.ptr(keymax), lib.stream_ptr())
-        prep = PreparedRows(raw, hi, lo, key, sqn, owner=data, keymax=keymax)
+            err = torch.empty((n,), dtype=torch.float32, device=self.device)
+            errmax = torch.empty((1,), dtype=torch.float32, device=self.device)
+            lib.call("kb2_split_error_terms", lib.ptr(lo), n, dpad, lib.ptr(err), lib.ptr(errmax),
+                     lib.stream_ptr())
+        prep = PreparedRows(raw, hi, lo, key, sqn, owner=data, keymax=keymax, err=err, errmax=errmax)
         if cache:
             self._prepared[id(data)] = prep
         return prep
@@ -374,27 +394,54 @@ class B200Mixin:
         return self._lib.lib.kb2_screen_stages(q.dpad, cap, int(dual)) > 0
 
     # The screen pays off while the proof holds for most rows.  On data whose neighbour gaps are
-    # below the TF32 error bound (tight clusters of normalised vectors) nearly every row would be
-    # searched twice, so with precision="auto" the first rows of a fit are a PROBE: if more than
-    # SCREEN_MAX_UNVERIFIED of them fail the proof, the rest of the fit uses the 3xTF32 kernels.
+    # around the TF32 error bound (tight clusters of normalised vectors) many rows would be
+    # searched twice, so with precision="auto" the first rows of a fit are a PROBE:
+    #   <= SCREEN_BOOST_UNVERIFIED of them unproven -> carry on;
+    #   more -> restart with LONGER lists (`_boosted_capacity`: the proof needs the gap between
+    #           the k-th and the cap-th neighbour to exceed E, and that gap grows with cap);
+    #   still > SCREEN_MAX_UNVERIFIED with the longer lists -> the rest of the fit uses 3xTF32.
+    SCREEN_BOOST_UNVERIFIED = 0.04
     SCREEN_MAX_UNVERIFIED = 0.25
     SCREEN_PROBE_ROWS = 18944            # one-direction search: 2 x 128 rows for each of 74 CTA pairs
 
-    def _screen_verdict(self, unverified) -> bool:
-        """Record (once per fit) whether the screen stays on, from the `unverified` flags of the
-        probe rows; one host sync."""
+    @staticmethod
+    def _boosted_capacity(cap: int) -> int:
+        """Longer candidate lists for fits whose probe leaves too many rows unproven."""
+        return min(64, (cap * 3 // 2 + 7) // 8 * 8) if cap < 64 else cap
+
+    def _capacity(self, c: int, q: PreparedRows = None, dual: bool = False) -> int:
+        """List length of the candidate search for `c` wanted neighbours (boosted by the probe)."""
+        cap = candidate_capacity(c)
+        if self._screen_boost and self.precision != "tf32x3":
+            boosted = self._boosted_capacity(cap)
+            if q is None or self._lib.lib.kb2_screen_stages(q.dpad, boosted, int(dual)) > 0:
+                cap = boosted
+        return cap
+
+    def _screen_verdict(self, unverified, cap: int = 0, dpad: int = 0, dual: bool = False) -> bool:
+        """Record (once per fit and list length) whether the screen carries on as configured,
+        from the `unverified` flags of the probe rows; one host sync.  False = start over
+        (`_screen_boost` or `_screen_ok` changed)."""
         if self.precision != "auto":
             return True
         if self._screen_ok is None:
             frac = float(unverified.to(torch.float32).mean()) if unverified.numel() else 0.0
+            self.search_stats.setdefault("screen_probe_unverified", []).append(frac)
+            can_boost = (not self._screen_boost and cap > 0 and self._boosted_capacity(cap) > cap
+                         and self._lib.lib.kb2_screen_stages(dpad, self._boosted_capacity(cap),
+                                                             int(dual)) > 0)
+            if frac > self.SCREEN_BOOST_UNVERIFIED and can_boost:
+                self._screen_boost = True          # verdict stays open: the longer lists are probed next
+                return False
             self._screen_ok = frac <= self.SCREEN_MAX_UNVERIFIED
-            self.search_stats["screen_probe_unverified"] = frac
         return self._screen_ok
 
-    def _eps_dot(self, dpad: int) -> float:
-        """Relative bound of |<hi(q), hi(y)> (fp32 accumulate) - <q, y>| / (|q| |y|): both
-        operands rounded to TF32 (2^-11 each, cross term), fp32 centring, accumulation."""
-        return 2.0 ** -10 * (1 + 2.0 ** -9) + dpad * 2.0 ** -23 + 2.0 ** -21
+    def _eps_acc(self, dpad: int) -> float:
+        """Bound of the accumulation error of <hi(q), hi(y)> relative to |q| |y|: the TF32
+        products are exact in fp32, dpad additions of unknown order (truncation allowed), plus
+        the fp32 rounding of the centring.  The operand rounding itself enters the proof
+        through the measured error norms (kb2_split_error_terms), see refine.cu."""
+        return dpad * 2.0 ** -22 + 2.0 ** -21
 
     def _screen_plan(self, nq: int, ny: int, dpad: int, cap: int):
         import ctypes as C
@@ -451,8 +498,8 @@ class B200Mixin:
                  y.raw.stride(0), q.d, 4, lib.ptr(q.sqnorm), lib.ptr(y.sqnorm), lib.ptr(cand),
                  cand.shape[1], self._metric_code, y.base, int(exclude_self), y.base - q.base, k,
                  lib.ptr(out_d), lib.ptr(out_i), tau, tau_row_stride, tau_step, tau_count,
-                 lib.ptr(q.key), lib.ptr(y.keymax), self._eps_dot(q.dpad), lib.ptr(unverified),
-                 lib.stream_ptr())
+                 lib.ptr(q.key), lib.ptr(y.keymax), lib.ptr(q.err), lib.ptr(y.errmax),
+                 self._eps_acc(q.dpad), lib.ptr(unverified), lib.stream_ptr())
         return out_d, out_i, unverified
 
     def _research(self, q: PreparedRows, y: PreparedRows, bad, k: int, exclude_self: bool,
@@ -501,9 +548,12 @@ class B200Mixin:
         # problems large enough to amortise the threshold sample
         if cap > 32 or rows.dpad < 192 or rows.n * cols.n < (1 << 32):
             return False
+        # the column buffers must fit; decided from rank-independent quantities only (shapes,
+        # world size, the device's TOTAL memory) so that every rank of a distributed run takes
+        # the same branch -- the branches issue different collectives
         world = torch.distributed.get_world_size() if self.distributed else 1
-        free, _total = torch.cuda.mem_get_info(self.device)
-        return (cols.n // world + 1) * self._fused_col_cap(cap) * 8 < 0.4 * free
+        total = torch.cuda.get_device_properties(self.device).total_memory
+        return (cols.n // world + 1) * self._fused_col_cap(cap) * 8 < 0.2 * total
 
     def _fused_col_cap(self, cap: int) -> int:
         return max(self.FUSED_COL_CAP, cap)
@@ -532,7 +582,7 @@ class B200Mixin:
         (dist, ind) of every column's k_cols nearest rows)."""
         lib = self._lib
         dev = self.device
-        cap = candidate_capacity(max(k_rows, k_cols))
+        cap = self._capacity(max(k_rows, k_cols), rows, dual=True)
         with torch.cuda.device(dev):
             st = lib.stream_ptr()
             sm = torch.cuda.get_device_properties(dev).multi_processor_count
@@ -582,8 +632,10 @@ class B200Mixin:
                                          lib.ptr(key_rows) + 4 * (cap - 1), r_lists * cap, cap, r_lists,
                                          out=(fwd_d[lo:hi], fwd_i[lo:hi], unv_rows[lo:hi]))
                     del key_rows
-                    if lo == 0 and len(bounds) > 2 and not self._screen_verdict(unv_rows[lo:hi]):
-                        # probe failed: start over with 3xTF32 keys (_use_screen now says no)
+                    if lo == 0 and len(bounds) > 2 and not self._screen_verdict(
+                            unv_rows[lo:hi], cap, rows.dpad, dual=True):
+                        # probe failed: start over with longer lists, or with 3xTF32 keys
+                        # (_capacity / _use_screen now answer differently)
                         del cand_rows, col_buf, col_cnt, fwd_d, fwd_i, unv_rows, tau
                         return self.search_both(rows, cols, k_rows, k_cols,
                                                 exclude_self_rows=exclude_self_rows)
@@ -613,8 +665,8 @@ class B200Mixin:
                         emitted -= torch.where(col_cnt < (1 << 30), col_cnt, 0).sum()
             if screen:
                 self.search_stats["screen_rows"] += rows.n
-                self._research(rows, cols, torch.nonzero(unv_rows).flatten(), k_rows,
-                               exclude_self_rows, fwd_d, fwd_i)
+                bad_rows = torch.nonzero(unv_rows).flatten()
+                self._research(rows, cols, bad_rows, k_rows, exclude_self_rows, fwd_d, fwd_i)
             fwd = (fwd_d, fwd_i)
             # 3. column side: best cap emitted rows per column, exact finish
             cand_cols = torch.empty((cols.n, cap), dtype=torch.int32, device=dev)
@@ -630,11 +682,16 @@ class B200Mixin:
                 self.search_stats["screen_rows"] += cols.n
                 n_over = int(overflow.sum()) if stats else 0
                 # overflowed columns lost rows below their threshold: search them again too
-                self._research(cols, rows, torch.nonzero(unv | overflow).flatten(), k_cols, False,
-                               rev_d, rev_i)
+                bad_cols = torch.nonzero(unv | overflow).flatten()
+                self._research(cols, rows, bad_cols, k_cols, False, rev_d, rev_i)
+                # local ids of the rows / columns that took the 3xTF32 re-search (parity samples
+                # of the tests and bench.py force-include them)
+                self.researched = {"rows": bad_rows + rows.base, "cols": bad_cols + cols.base}
             else:
                 rev_d, rev_i = self._refine(cols, rows, cand_cols, k_cols, False)
-                bad = torch.nonzero(overflow).flatten()
+                # overflowed columns lost rows; a column whose threshold TIES with its cap-th
+                # best key (duplicate rows: emits are strictly below tau) may hold fewer than k
+                bad = torch.nonzero(overflow.bool() | (rev_i[:, k_cols - 1] < 0)).flatten()
                 n_over = int(bad.numel())
                 if bad.numel():      # columns whose buffer overflowed: plain search for those few
                     d_b, i_b = self._search_tf32x3(cols.take(bad), rows, k_cols)
@@ -674,7 +731,7 @@ class B200Mixin:
         lib = self._lib
         if q.d != y.d:
             raise ValueError(f"query has {q.d} features, index has {y.d}")
-        cap = min(candidate_capacity(k), lib.lib.kb2_max_candidates())
+        cap = min(self._capacity(k, q), lib.lib.kb2_max_candidates())
         if k > cap:
             raise ValueError(
                 f"B200 supports at most {lib.lib.kb2_max_candidates()} neighbours per "
@@ -703,10 +760,13 @@ class B200Mixin:
                 self._refine_checked(part, y, cand, k, exclude_self, lib.ptr(ckey) + 4 * (cap - 1),
                                      lists * cap, cap, lists,
                                      out=(out_d[lo:hi], out_i[lo:hi], unv[lo:hi]))
-                self.search_stats["screen_rows"] += hi - lo
                 del cand, ckey
-                if len(parts) > 1 and lo == 0:
-                    self._screen_verdict(unv[lo:hi])
+                if len(parts) > 1 and lo == 0 and not self._screen_verdict(unv[lo:hi], cap, q.dpad) \
+                        and self._screen_ok is None:
+                    # the probe asks for longer lists: start over (3xTF32 verdicts carry on below)
+                    del out_d, out_i, unv
+                    return self.search(q, y, k, exclude_self=exclude_self)
+                self.search_stats["screen_rows"] += hi - lo
             self._research(q, y, torch.nonzero(unv).flatten(), k, exclude_self, out_d, out_i)
         return out_d, out_i
 

@@ -410,6 +410,26 @@ def _row_mismatch(dist, ind, ref_dist, ref_ind, rtol, atol):
     return None
 
 
+def count_mismatched_rows(dist, ind, ref_dist, ref_ind, rtol=1e-5, atol=1e-9):
+    """Number of rows that differ from the oracle beyond the tie tolerance of
+    `assert_neighbors_match` (bench.py's `parity_check.mismatch`), and the first message."""
+    dist = np.asarray(dist, dtype=np.float64)
+    ref_dist = np.asarray(ref_dist, dtype=np.float64)
+    ind, ref_ind = np.asarray(ind), np.asarray(ref_ind)
+    if dist.shape != ref_dist.shape or ind.shape != ref_ind.shape:
+        return dist.shape[0], f"shape {dist.shape} vs {ref_dist.shape}"
+    with np.errstate(invalid="ignore"):
+        suspicious = ~np.isclose(dist, ref_dist, rtol=rtol, atol=atol, equal_nan=True)
+    suspicious |= ind != ref_ind
+    bad, first = 0, None
+    for r in np.flatnonzero(suspicious.any(axis=1)):
+        msg = _row_mismatch(dist[r], ind[r], ref_dist[r], ref_ind[r], rtol, atol)
+        if msg is not None:
+            bad += 1
+            first = first or f"row {int(r)}: {msg}"
+    return bad, first
+
+
 def assert_neighbors_match(dist, ind, ref_dist, ref_ind, rtol=1e-5, atol=1e-9,
                            what="", max_bad_rows=0.0):
     """Indices must be identical except where the oracle's distances at the

@@ -16,8 +16,10 @@ The three shims below are applied at *import time only*; no file under
 
 * by ``oracle/make_golden.py`` to generate the committed fixtures under
   ``tests/golden/`` from the real reference, and
-* by ``tests/test_oracle_vs_reference.py`` (skipped automatically when
-  /root/reference is absent, e.g. on the GPU box)
+* by ``tests/test_oracle_vs_reference.py`` and the plugin tests (skipped automatically when
+  no copy of the reference is present), and
+* by ``bench.py --impl reference``, which drives the reference's own ``Kiez`` from the
+  unmodified copy under ``baseline/_ref`` (tools/vendor_reference.sh)
 
 so that the numpy restatement in ``oracle/kiez_oracle.py`` is *pinned* against
 outputs of the reference itself.  Nothing in the product package imports it.
@@ -30,7 +32,23 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("KIEZ_REFERENCE_ROOT", "/root/reference")
+_VENDORED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                         "baseline", "_ref")
+
+
+def _find_reference_root() -> str:
+    """/root/reference in the authoring container; on the GPU box the unmodified copy that
+    tools/vendor_reference.sh placed under baseline/_ref (git-ignored, travels with gpurun)."""
+    env = os.environ.get("KIEZ_REFERENCE_ROOT")
+    if env:
+        return env
+    for root in ("/root/reference", _VENDORED):
+        if os.path.isdir(os.path.join(root, "kiez")):
+            return root
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 
 def reference_available() -> bool:

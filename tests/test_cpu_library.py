@@ -48,7 +48,7 @@ def test_pure_host_entry_points():
     from kiez_b200 import _lib
 
     lib = _lib.lib
-    assert lib.kb2_version() == 3
+    assert lib.kb2_version() == 4
     assert lib.kb2_max_candidates() == 128
     assert [lib.kb2_padded_dim(d) for d in (1, 32, 33, 50, 256)] == [32, 32, 64, 64, 256]
     # plenty of query tiles: never split; few query tiles: split to fill 148 SMs

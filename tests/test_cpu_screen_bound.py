@@ -1,5 +1,5 @@
 """not gpu: the error bound E behind the screen's completeness proof (csrc/refine.cu,
-refine_topk_kernel<CHECK>; B200._eps_dot) against a numpy emulation of the screen's arithmetic:
+refine_topk_kernel<CHECK>; B200._eps_acc, kb2_split_error_terms) against a numpy emulation of the screen's arithmetic:
 operands centred in fp32 and rounded to TF32 (cvt.rna: 10 mantissa bits, ties away, prep.cu),
 products accumulated in fp32, key terms rounded to fp32.  If |screen key - exact key| <= E for
 every (query, index) pair, "exact k-th key < tau - E" proves that no row outside the proposal
@@ -15,9 +15,26 @@ def to_tf32(x):
     return ((u + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
 
 
-def eps_dot(dpad):
-    """B200._eps_dot (kiez_b200/neighbors.py)."""
-    return 2.0 ** -10 * (1 + 2.0 ** -9) + dpad * 2.0 ** -23 + 2.0 ** -21
+def eps_acc(dpad):
+    """B200._eps_acc (kiez_b200/neighbors.py)."""
+    return dpad * 2.0 ** -22 + 2.0 ** -21
+
+
+def split_error_terms(w):
+    """kb2_split_error_terms (prep.cu): upper bound of ||w - hi||^2 per row from lo = tf32(w - hi)."""
+    lo = to_tf32((w - to_tf32(w)).astype(np.float32))
+    acc = (lo.astype(np.float64) ** 2).sum(axis=1) * (1.0 + 2.0 ** -9) * (1.0 + 2.0 ** -20)
+    out = acc.astype(np.float32)
+    return np.where(out.astype(np.float64) < acc, np.nextafter(out, np.float32(np.inf)), out)
+
+
+def proof_bound(qn2, ym2, q_err, y_err_max, dpad):
+    """E of refine.cu from the fp32 inputs the kernel reads."""
+    up = 1.000001
+    qn, ym = np.sqrt(qn2) * up, np.sqrt(ym2) * up
+    dq, dym = np.sqrt(q_err.astype(np.float64)) * up, np.sqrt(float(y_err_max)) * up
+    return (2.0 * (dq * ym + qn * (1.0 + 2.0 ** -11) * dym + eps_acc(dpad) * qn * ym)
+            + 4.76837158203125e-07 * (ym2 + 2.0 * qn * ym))
 
 
 def screen_keys(q, y, center, order):
@@ -35,7 +52,7 @@ def screen_keys(q, y, center, order):
             dot = (dot + (qh[:, k0:k0 + 8].astype(np.float64)
                           @ yh[:, k0:k0 + 8].T.astype(np.float64)).astype(np.float32)).astype(np.float32)
     key = (y_key[None, :] + (np.float32(-2.0) * dot)).astype(np.float32)
-    return key, q_key, y_key
+    return key, q_key, y_key, split_error_terms(qc), split_error_terms(yc)
 
 
 def data(kind, n, d, rng):
@@ -58,15 +75,12 @@ def test_screen_key_error_is_within_the_proof_bound(kind, d, order):
     q = data(kind, 96, d, rng).astype(np.float32)
     y = data(kind, 700, d, rng).astype(np.float32)
     center = y.mean(axis=0, dtype=np.float64).astype(np.float32)       # B200._center_vec
-    key, q_key, y_key = screen_keys(q, y, center, order)
+    key, q_key, y_key, q_err, y_err = screen_keys(q, y, center, order)
     q64, y64 = q.astype(np.float64), y.astype(np.float64)
     d2 = ((q64[:, None, :] - y64[None, :, :]) ** 2).sum(axis=2)        # what the exact finish computes
     exact_key = d2 - q_key.astype(np.float64)[:, None]
-    # E as in refine.cu (euclidean branch): qn, ym inflated by 1e-6, key_max = max ||y-c||^2
-    qn = np.sqrt(q_key.astype(np.float64)) * 1.000001
-    ym2 = float(y_key.max())
-    ym = np.sqrt(ym2) * 1.000001
-    E = 2.0 * eps_dot(d) * qn * ym + 4.76837158203125e-07 * (ym2 + 2.0 * qn * ym)
+    # E as in refine.cu (euclidean branch): norms inflated by 1e-6, key_max = max ||y-c||^2
+    E = proof_bound(q_key.astype(np.float64), float(y_key.max()), q_err, y_err.max(), d)
     # the proof also gives away 2.4e-7 * ||q-c||^2 for the fp32 rounding of q_key
     slack = E + 2.4e-7 * q_key.astype(np.float64)
     err = np.abs(key.astype(np.float64) - exact_key)
@@ -74,6 +88,12 @@ def test_screen_key_error_is_within_the_proof_bound(kind, d, order):
     assert ratio <= 1.0, f"{kind} d={d}: |screen - exact| exceeds E by {ratio:.3f}x"
     # and the bound is not vacuous: within ~2 orders of magnitude of the observed error
     assert ratio > 1e-3, f"{kind} d={d}: bound {1 / ratio:.0f}x looser than any observed error"
+    # the measured-rounding-error bound is what lets clustered data pass the proof: at least 2x
+    # tighter than the operand-independent 2^-10 ||q|| ||y|| bound it replaced
+    qn = np.sqrt(q_key.astype(np.float64))
+    old = 2.0 * (2.0 ** -10 + d * 2.0 ** -23) * qn * np.sqrt(float(y_key.max()))
+    assert np.median(E / old) < 0.55 and (E / old).max() < 0.75
+    print(f'{kind} d={d} {order}: max err/E {ratio:.3f}, E/old median {np.median(E / old):.3f}')
 
 
 def test_tf32_rounding_emulation():
@@ -95,7 +115,7 @@ def test_tf32_rounding_emulation():
 def test_cosine_screen_key_error_is_within_the_proof_bound(kind, d):
     """Cosine branch of the proof (refine.cu): rows are L2-normalised in fp32 before the TF32
     rounding (prep.cu, normalize = 1), key = -2 <q^, y^>, exact key = 2 (cosine distance - 1),
-    E = 2 eps + 1e-6."""
+    E as in the euclidean branch with unit norms, + 1e-6."""
     rng = np.random.default_rng(3 * d + len(kind))
     q = data(kind, 96, d, rng).astype(np.float32)
     y = data(kind, 700, d, rng).astype(np.float32)
@@ -103,10 +123,11 @@ def test_cosine_screen_key_error_is_within_the_proof_bound(kind, d):
     def prep(x):
         n2 = (x.astype(np.float64) ** 2).sum(axis=1)
         scale = (1.0 / np.sqrt(n2)).astype(np.float32)
-        return to_tf32((x * scale[:, None]).astype(np.float32))
+        w = (x * scale[:, None]).astype(np.float32)
+        return to_tf32(w), split_error_terms(w)
 
     dot = np.zeros((q.shape[0], y.shape[0]), dtype=np.float32)
-    qh, yh = prep(q), prep(y)
+    (qh, q_err), (yh, y_err) = prep(q), prep(y)
     for k0 in range(0, d, 8):
         dot = (dot + (qh[:, k0:k0 + 8].astype(np.float64)
                       @ yh[:, k0:k0 + 8].T.astype(np.float64)).astype(np.float32)).astype(np.float32)
@@ -114,7 +135,7 @@ def test_cosine_screen_key_error_is_within_the_proof_bound(kind, d):
     q64, y64 = q.astype(np.float64), y.astype(np.float64)
     cos = (q64 @ y64.T) / np.outer(np.linalg.norm(q64, axis=1), np.linalg.norm(y64, axis=1))
     exact_key = 2.0 * ((1.0 - cos) - 1.0)
-    E = 2.0 * eps_dot(d) * 1.000001 + 1e-6
-    ratio = (np.abs(key - exact_key) / E).max()
+    E = proof_bound(np.ones(q.shape[0]), 1.0, q_err, y_err.max(), d) + 1e-6
+    ratio = (np.abs(key - exact_key) / E[:, None]).max()
     assert ratio <= 1.0, f"{kind} d={d}: cosine screen error exceeds E by {ratio:.3f}x"
     assert ratio > 1e-3

@@ -48,10 +48,24 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert line["impl"] == "reference" and line["higher_is_better"] is True
     assert line["metric"] == "queries_per_s" and line["unit"] == "queries/s"
     assert line["value"] > 0 and line["n_gpus"] == 1 and line["steps"] == 1
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    # the unmodified reference (baseline/_ref or /root/reference) when a copy is present
+    from oracle import ref_shim
+    assert line["cpu_baseline"]["kind"] == ("reference" if ref_shim.reference_available() else "port")
+    assert line["cpu_baseline"]["cores"] >= 1 and line["warmup"] == 1
+    assert set(line["config"]) >= {"workload", "precision", "fused", "parallelism"}
     assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "600x500" in line["config"]["workload"]
+
+
+def test_bench_reference_arm_port_fallback():
+    import json
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                          "--workload", "c1", "--steps", "1", "--warmup", "0", "--cpu-kind", "port"],
+                         capture_output=True, text=True, check=True, timeout=300).stdout
+    line = json.loads(out.strip())
+    assert line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
 
 
 def test_bench_reference_arm_other_ranks_stay_silent():

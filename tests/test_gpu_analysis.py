@@ -74,3 +74,12 @@ def test_hits():
     big = rng.integers(0, 1000, (50000, 10))
     gold = rng.integers(0, 1000, 50000)
     assert hits(big, gold, k=(1, 5, 10)) == pytest.approx(O.hits(big, gold, k=(1, 5, 10)))
+    # the reference's corner cases (eval_metrics.py:8-12,53-61): k=None -> [1, 5, 10]; the
+    # denominator is len(gold), so a key that is not a row counts as a miss; list / dict input
+    doc = np.array([[1, 2, 3], [2, 3, 4], [3, 4, 5], [4, 5, 6]])
+    assert hits(doc, {0: 2, 1: 4, 2: 3, 3: 4}) == {1: 0.5, 5: 1.0, 10: 1.0}     # its docstring example
+    assert hits(doc.tolist(), {0: 2, 1: 4, 2: 3, 3: 4}, k=[5, 1]) == {1: 0.5, 5: 1.0}
+    assert hits(doc, {0: 2, 1: 4, 99: 7, -1: 3}, k=[1, 3]) == {1: 0.0, 3: 0.5}
+    assert hits({10: [1, 2, 3], 11: [2, 3, 4]}, {10: 2, 11: 2, 12: 0}, k=[1, 2]) == \
+        {1: 1 / 3, 2: 2 / 3}
+    assert hits(doc, np.array([1, 4]), k=[1, 3]) == {1: 0.5, 3: 1.0}            # short gold array

@@ -147,9 +147,12 @@ CONFIG_SHAPED = [
 ]
 
 
+CONFIG_SEEDS = {name: 101 + i for i, (name, *_rest) in enumerate(CONFIG_SHAPED)}
+
+
 @pytest.mark.parametrize(("name", "n", "m", "d", "c", "k", "hub"), CONFIG_SHAPED)
 def test_config_shaped_parity(name, n, m, d, c, k, hub):
-    rng = np.random.default_rng(abs(hash(name)) % 1000)
+    rng = np.random.default_rng(CONFIG_SEEDS[name])      # fixed: str hashes are salted per process
     source = rng.standard_normal((n, d)).astype(np.float32)
     target = rng.standard_normal((m, d)).astype(np.float32)
     want_d, want_i = O.kiez_kneighbors(source.astype(np.float64), target.astype(np.float64),
@@ -232,21 +235,40 @@ def test_full_size_c4_sampled_parity():
     rev_dist, rev_ind = inst.hubness.r_dist_train_, inst.hubness.r_ind_train_
     assert (torch.diff(rev_dist, dim=1) >= 0).all()
     assert int(rev_ind.min()) >= 0 and int(rev_ind.max()) < n
-    # oracle on a row sample (rows from every row segment of the pass)
-    rows = np.sort(np.random.default_rng(1).choice(n, 48, replace=False))
+    # oracle on >= 4096 rows per direction: stratified over the row segments of the pass, plus
+    # EVERY row / column whose proof failed (they took the 3xTF32 re-search)
+    rng = np.random.default_rng(1)
+    bounds = algo._fused_segments(n, algo._fused_sample_rows(n, 16))
+    per_seg = -(-4096 // (len(bounds) - 1))
+    rows = np.concatenate([rng.choice(np.arange(lo, hi), min(per_seg, hi - lo), replace=False)
+                           for lo, hi in zip(bounds[:-1], bounds[1:])])
+    researched = {key: val.cpu().numpy() for key, val in algo.researched.items()}
+    assert len(researched["rows"]) + len(researched["cols"]) == algo.search_stats["screen_unverified"]
+    rows = np.unique(np.concatenate([rows, researched["rows"]]))
     s64 = source.cpu().numpy().astype(np.float64)
     t64 = target.cpu().numpy().astype(np.float64)
     fwd_d, fwd_i = O.knn_sklearn(s64[rows], t64, c, n_jobs=-1)
-    touched = np.unique(fwd_i)
-    want_rev_d, want_rev_i = O.knn_sklearn(t64[touched], s64, c, n_jobs=-1)
-    O.assert_neighbors_match(rev_dist[touched].cpu().numpy(), rev_ind[touched].cpu().numpy(),
-                             want_rev_d, want_rev_i, RTOL, ATOL, what="c4 reverse (column side)")
+    got_fd, got_fi = algo.kneighbors(k=c)                      # forward kNN before the rescale
+    O.assert_neighbors_match(got_fd[rows].cpu().numpy(), got_fi[rows].cpu().numpy(), fwd_d, fwd_i,
+                             RTOL, ATOL, what=f"c4 forward kNN ({len(rows)} rows)")
+    # reverse: 4096 sampled columns + the re-searched ones + everything 64 of the rows touch
+    # (their CSLS value needs the reverse statistics of all their candidates)
+    csls_rows = rows[rng.choice(len(rows), 64, replace=False)]
+    touched = np.unique(fwd_i[np.isin(rows, csls_rows)])
+    cols = np.unique(np.concatenate([rng.choice(m, 4096, replace=False), researched["cols"], touched]))
+    want_rev_d, want_rev_i = O.knn_sklearn(t64[cols], s64, c, n_jobs=-1)
+    O.assert_neighbors_match(rev_dist[cols].cpu().numpy(), rev_ind[cols].cpu().numpy(),
+                             want_rev_d, want_rev_i, RTOL, ATOL,
+                             what=f"c4 reverse kNN (column side, {len(cols)} columns)")
     r_train = np.zeros(m)
-    r_train[touched] = want_rev_d.mean(axis=1)
-    want = 2 * fwd_d - fwd_d.mean(axis=1, keepdims=True) - r_train[fwd_i]
-    want_d, want_i = O.sort_topk(want, fwd_i, k)
-    O.assert_neighbors_match(dist[rows].cpu().numpy(), ind[rows].cpu().numpy(), want_d, want_i,
-                             RTOL, ATOL, what="c4 forward + CSLS")
+    r_train[cols] = want_rev_d.mean(axis=1)
+    sel = np.isin(rows, csls_rows)
+    want = 2 * fwd_d[sel] - fwd_d[sel].mean(axis=1, keepdims=True) - r_train[fwd_i[sel]]
+    want_d, want_i = O.sort_topk(want, fwd_i[sel], k)
+    O.assert_neighbors_match(dist[rows[sel]].cpu().numpy(), ind[rows[sel]].cpu().numpy(), want_d,
+                             want_i, RTOL, ATOL, what="c4 forward + CSLS")
+    print(f"c4 full size: {len(rows)} rows + {len(cols)} columns checked, "
+          f"{len(researched['rows'])} + {len(researched['cols'])} of them re-searched")
     scores = hubness_score(ind, m, k=k, store_k_occurrence=True)
     assert int(scores["k_occurrence"].sum()) == n * k          # checksum of the histogram
 

@@ -244,7 +244,7 @@ def test_screen_unproven_rows_are_searched_again(single):
     3xTF32 re-search (self-exclusion included) and still equal the oracle."""
     q, y = _data(900, 1200, 48, seed=22)
     algo = _algo(n_candidates=8, impl="screen")
-    algo._eps_dot = lambda dpad: 5.0
+    algo._eps_acc = lambda dpad: 0.9
     if single:
         algo.fit(q)
         y = q
@@ -340,8 +340,10 @@ def test_screen_probe_one_direction(tight):
     algo.fit(q, y)
     dist, ind = algo.kneighbors(k=k)
     assert algo._screen_ok is (not tight), algo.search_stats
+    probes = algo.search_stats["screen_probe_unverified"]
     if tight:
-        assert algo.search_stats["screen_probe_unverified"] > 0.25
+        # the probe ran twice (cap 16, then the boosted lists) and both left most rows unproven
+        assert len(probes) == 2 and min(probes) > 0.25 and algo._screen_boost
         assert algo.search_stats["screen_rows"] == 512          # only the probe was screened
     else:
         assert algo.search_stats["screen_rows"] == nq
@@ -355,7 +357,69 @@ def test_screen_probe_one_direction(tight):
     O.assert_neighbors_match(dist2.cpu().numpy(), ind2.cpu().numpy(), want_d, want_i, RTOL, ATOL,
                              what=f"probe reverse tight={tight}")
     algo.fit(q, y)
-    assert algo._screen_ok is None
+    assert algo._screen_ok is None and not algo._screen_boost
+
+
+def _dense_clusters(n, d, seed, clusters=3, noise=0.25):
+    """bench.py's "hubby" distribution (unit-normalised Gaussian mixture, relative noise 0.25) with
+    few clusters, so that a cluster is as densely populated as at the 1M-row size: the gap
+    between the k-th and the 16th neighbour is around the proof's error bound E."""
+    rng = np.random.default_rng(seed)
+    cent = np.random.default_rng(77).standard_normal((clusters, d))
+    x = noise * rng.standard_normal((n, d)) + cent[rng.integers(0, clusters, n)]
+    return (x / np.linalg.norm(x, axis=1, keepdims=True)).astype(np.float32)
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_screen_probe_boosts_the_list_length(fused):
+    """Neighbour gaps around E: the probe asks for longer candidate lists (`_screen_boost`)
+    instead of giving up the screen; results stay exact whatever the verdicts are."""
+    from kiez_b200 import B200
+
+    nq, ny, d, k = 12000, 10000, 256, 10
+    q, y = _dense_clusters(nq, d, 1), _dense_clusters(ny, d, 2)
+    algo = B200(n_candidates=k, fused=fused)
+    algo.SCREEN_PROBE_ROWS = 2048
+    algo.FUSED_SEGMENT_MIN_ROWS = 1024
+    algo.fit(q, y)
+    rd, ri = algo.kneighbors(k=k, query=y, s_to_t=False)       # kiez's reverse pass first
+    fd, fi = algo.kneighbors(k=k)
+    probes = algo.search_stats["screen_probe_unverified"]
+    print("probe fractions", probes, "boost", algo._screen_boost, "screen_ok", algo._screen_ok,
+          algo.search_stats)
+    assert len(probes) == (2 if algo._screen_boost else 1)
+    if algo._screen_boost:
+        assert probes[0] > algo.SCREEN_BOOST_UNVERIFIED and probes[1] < probes[0]
+    q64, y64 = q.astype(np.float64), y.astype(np.float64)
+    want_d, want_i = O.knn_brute(q64, y64, k, "euclidean")
+    O.assert_neighbors_match(fd.cpu().numpy(), fi.cpu().numpy(), want_d, want_i, RTOL, ATOL, what="fwd")
+    want_d, want_i = O.knn_brute(y64, q64, k, "euclidean")
+    O.assert_neighbors_match(rd.cpu().numpy(), ri.cpu().numpy(), want_d, want_i, RTOL, ATOL, what="rev")
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "auto"])
+def test_fused_duplicate_rows_tie_with_the_thresholds(precision):
+    """Several hundred identical source rows: a column's threshold (cap-th best key of the row
+    sample) ties exactly with its best keys, and emits are strictly below the threshold, so the
+    column may receive fewer than k rows -- it must be searched again, never padded with -1."""
+    from kiez_b200 import B200
+
+    rng = np.random.default_rng(31)
+    nq, ny, d, c = 4000, 900, 64, 10
+    q = rng.standard_normal((nq, d)).astype(np.float32)
+    q[::5] = q[0]                                   # 800 copies of one row, spread over the sample
+    y = rng.standard_normal((ny, d)).astype(np.float32)
+    y[:50] = q[0] + 0.01 * rng.standard_normal((50, d)).astype(np.float32)   # their neighbours
+    algo = B200(n_candidates=c, fused=True, precision=precision)
+    algo.FUSED_SEGMENT_MIN_ROWS = 512
+    qp, yp = algo._prepare(q, cache=False), algo._prepare(y, cache=False)
+    (fd, fi), (rd, ri) = algo.search_both(qp, yp, c, c)
+    assert int(ri.min()) >= 0 and int(fi.min()) >= 0 and bool(torch.isfinite(rd).all())
+    q64, y64 = q.astype(np.float64), y.astype(np.float64)
+    want_d, want_i = O.knn_brute(y64, q64, c, "euclidean")
+    np.testing.assert_allclose(rd.cpu().numpy(), want_d, rtol=RTOL, atol=ATOL)
+    want_d, want_i = O.knn_brute(q64, y64, c, "euclidean")
+    O.assert_neighbors_match(fd.cpu().numpy(), fi.cpu().numpy(), want_d, want_i, RTOL, ATOL, what="fwd")
 
 
 @pytest.mark.parametrize("tight", [False, True])
