@@ -145,10 +145,14 @@ int kb2_col_compact(uint64_t *col_buf, uint32_t *col_cnt, int64_t ny, int col_ca
  *   dual-direction form when tau_col != NULL: additionally appends to col_buf/col_cnt like
  *     kb2_knn_fused (q_key = the row-side selection terms, row_id_base = first row of the
  *     segment).
- * kb2_screen_stages: pipeline stages the kernel gets for (dpad, cap); 0 = shape not
- *   supported (dpad > 256 or lists too long for the shared memory left by the query tile).
+ * kb2_screen_stages: ring slots (16 KB each) the kernel gets for (dpad, cap); 0 = shape not
+ *   supported (dpad > 1024, cap > 128).  kb2_screen_config additionally reports the append-buffer
+ *   slots per list and how many of the dpad/32 K chunks of the query tile stay resident in
+ *   shared memory (the rest is streamed through the ring with the index tiles); max_smem <= 0 =
+ *   the current device's opt-in limit (pass 232448 to evaluate the B200 plan without a device).
  */
 int kb2_screen_stages(int dpad, int cap, int dual);
+int kb2_screen_config(int dpad, int cap, int dual, int max_smem, int *slots, int *resident);
 int kb2_screen_plan(int64_t nq, int64_t ny, int dpad, int cap, int sm_count, int *steps,
                     int *chained);
 int kb2_knn_screen(const float *q_hi, const float *q_key, int64_t nq, const float *y_hi,

@@ -1,6 +1,7 @@
 // Screening candidate search: ONE tcgen05.mma.kind::tf32 product per K step (the `hi` halves
-// of the 3xTF32 split only), query tile RESIDENT in shared memory, CTA pairs, index ranges
-// sized for L2 and chained per query tile.  One-direction (rows only) and dual-direction
+// of the 3xTF32 split only), query tile RESIDENT in shared memory (all of it, or its first
+// `resident` K chunks when long candidate lists or wide rows need the space), CTA pairs, index
+// ranges sized for L2 and chained per query tile.  One-direction (rows only) and dual-direction
 // (rows + per-column emits, as knn_fused.cu) forms of the same kernel.
 //
 // Why it is still exact: the kernel only proposes candidates.  The exact finish
@@ -25,10 +26,18 @@
 // index had been swept in one unit.  Without chaining (few query tiles: parallelism comes from
 // the ranges) every range writes its own list, like the `splits` of knn_tc2.cu.
 //
-// Protocol per unit: producer (warp PROD of both CTAs) waits q_empty, TMA-loads the query
-// tile's K chunks (bytes credited to CTA 0's q_full), then streams index half-tiles through
-// the stage ring exactly like knn_tc2.cu; the MMA issuer (CTA 0) waits q_full once per unit
-// and commits q_empty (multicast) after the unit's last MMA.
+// Protocol per unit: producer (warp PROD of both CTAs) waits q_empty, TMA-loads the resident
+// K chunks of the query tile (bytes credited to CTA 0's q_full), then streams index half-tiles
+// through the stage ring exactly like knn_tc2.cu; the MMA issuer (CTA 0) waits q_full once per
+// unit and commits q_empty (multicast) after the unit's last MMA.
+//
+// Partial residency (cap > 32 at d = 256, cap > 64, dpad > 256): the ring holds uniform 16 KB
+// slots, one TMA box each.  K chunk kc of an index tile takes one slot for the index half-tile
+// and, when kc >= resident, a second one for the query tile's chunk kc (re-read from L2 for
+// every index tile).  Per index tile the operand stream is (2 kchunks - resident) slots instead
+// of kchunks: e.g. d = 256, cap = 56, resident = 5 -> 11 x 16 KB per 4096 tensor cycles =
+// 43 B/clk/SM, where streaming the whole query tile (the 3xTF32 pair kernel with one product)
+// would need 64 B/clk/SM against the ~43 B/clk/SM the L2 delivers.
 #include "dual_common.cuh"
 
 namespace kb2 {
@@ -36,23 +45,12 @@ namespace kb2 {
 constexpr int S_BN = 256;        // index rows per tile of the CTA pair
 constexpr int S_HALF = 128;      // ... of which each CTA stages 128
 constexpr int S_BK = 32;         // K chunk: 128-byte swizzle rows
-constexpr int S_MAX_DPAD = 256;  // resident query tile: 128 rows x dpad fp32 <= 128 KB
-
-// Dual-direction form: 384 threads share the 64 K registers (168 each).  Experiment kept behind
-// a macro (off): the producer / MMA warpgroup (warps 8-11) gives registers to the two epilogue
-// warpgroups (setmaxnreg 56 / 224), which then keep the next chunk's tcgen05.ld in flight while
-// they test the current one, like the one-direction kernel.  Measured 49 % SLOWER at C4
-// (1402 vs 940 ms per step, profiles/r01_ab_experiments.md block I): two epilogue warps per
-// scheduler already hide the TMEM latency, and ptxas parks loop invariants on the stack around
-// setmaxnreg.
-#ifndef KB2_DUAL_SETMAXNREG
-#define KB2_DUAL_SETMAXNREG 0
-#endif
-constexpr bool DUAL_REGS = KB2_DUAL_SETMAXNREG != 0;
+constexpr int S_MAX_DPAD = 1024; // the resident part of the query tile adapts; eps_acc of the proof grows with dpad
 
 struct ScreenParams {
     int64_t nq, ny;
     int kchunks, cap, buf_slots, stages;
+    int resident;         // K chunks of the query tile kept in shared memory (<= kchunks)
     int steps;            // index ranges
     int chained;          // 1: ranges of a query tile run in order and carry its lists
     int64_t per_step;     // index rows per range (multiple of S_BN)
@@ -85,8 +83,8 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap map_q,
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char *q_base = smem;                                         // [kchunks][128 x 32 fp32]
-    unsigned char *stage_base = q_base + (size_t)P.kchunks * Cfg::A_BYTES;  // [stages][128 x 32 fp32]
+    unsigned char *q_base = smem;                                         // [resident][128 x 32 fp32]
+    unsigned char *stage_base = q_base + (size_t)P.resident * Cfg::A_BYTES; // [stages][128 x 32 fp32]
     // per epilogue warp a BN-float tile: warps 0-3 key_y, (DUAL) warps 4-7 tau_col
     float *tile_s = reinterpret_cast<float *>(stage_base + (size_t)P.stages * Cfg::B_BYTES);
     float *emit_key = tile_s + EPI_WARPS * BN;                            // DUAL: [4][EMIT_Q]
@@ -153,8 +151,6 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap map_q,
     const uint32_t tmem_empty_leader = smem_u32(tmem_empty) & PEER_BIT_MASK;
 
     if (warp >= EPI_WARPS) {
-    // producer / MMA warpgroup (DUAL: + two idle warps): 128 x 56 + 256 x 224 = 64 512 registers
-    if constexpr (DUAL && DUAL_REGS) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == PROD_WARP) {
         // ------------------------------------------------------ TMA producer (both CTAs)
         int stage = 0;
@@ -166,27 +162,35 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap map_q,
             const int64_t y_begin = (int64_t)step * P.per_step;
             const int64_t y_end = min(P.ny, y_begin + P.per_step);
             const int q_row0 = (int)(qt * BM);          // may lie past nq: TMA zero-fills
-            // the query tile of this unit: its region is free once the previous unit's MMAs retired
-            mbar_wait(q_empty, qphase ^ 1);
-            if (elect_one()) {
-                if (rank == 0) mbar_expect_tx(q_full, 2u * (uint32_t)P.kchunks * Cfg::A_BYTES);
-                for (int kc = 0; kc < P.kchunks; ++kc)
-                    tma_load_2d_pair(&map_q, q_u32 + (uint32_t)kc * Cfg::A_BYTES, qf, kc * BK, q_row0);
+            // the resident part of this unit's query tile: its region is free once the previous
+            // unit's MMAs retired
+            if (P.resident > 0) {
+                mbar_wait(q_empty, qphase ^ 1);
+                if (elect_one()) {
+                    if (rank == 0) mbar_expect_tx(q_full, 2u * (uint32_t)P.resident * Cfg::A_BYTES);
+                    for (int kc = 0; kc < P.resident; ++kc)
+                        tma_load_2d_pair(&map_q, q_u32 + (uint32_t)kc * Cfg::A_BYTES, qf, kc * BK, q_row0);
+                }
+                __syncwarp();
+                qphase ^= 1;
             }
-            __syncwarp();
-            qphase ^= 1;
             for (int64_t c0 = y_begin; c0 < y_end; c0 += BN) {
                 const int y_row0 = (int)c0 + (int)rank * S_HALF;
                 for (int kc = 0; kc < P.kchunks; ++kc) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    if (elect_one()) {
-                        const uint32_t st = stage_u32 + (uint32_t)stage * Cfg::B_BYTES;
-                        const uint32_t fb = (full_u32 + (uint32_t)stage * 8) & PEER_BIT_MASK;
-                        if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::B_BYTES);
-                        tma_load_2d_pair(&map_y, st, fb, kc * BK, y_row0);
+                    // one slot for the index half-tile, one more for a streamed query chunk
+                    const int loads = kc < P.resident ? 1 : 2;
+                    for (int l = 0; l < loads; ++l) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        if (elect_one()) {
+                            const uint32_t st = stage_u32 + (uint32_t)stage * Cfg::B_BYTES;
+                            const uint32_t fb = (full_u32 + (uint32_t)stage * 8) & PEER_BIT_MASK;
+                            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::B_BYTES);
+                            if (l == 0) tma_load_2d_pair(&map_y, st, fb, kc * BK, y_row0);
+                            else tma_load_2d_pair(&map_q, st, fb, kc * BK, q_row0);
+                        }
+                        __syncwarp();
+                        if (++stage == P.stages) { stage = 0; phase ^= 1; }
                     }
-                    __syncwarp();
-                    if (++stage == P.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -202,31 +206,43 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap map_q,
                 const int step = (int)(u / q_pairs);
                 const int64_t y_begin = (int64_t)step * P.per_step;
                 const int64_t y_end = min(P.ny, y_begin + P.per_step);
-                mbar_wait(q_full, qphase);
-                tc_fence_after();
-                qphase ^= 1;
+                if (P.resident > 0) {
+                    mbar_wait(q_full, qphase);
+                    tc_fence_after();
+                    qphase ^= 1;
+                }
                 for (int64_t c0 = y_begin; c0 < y_end; c0 += BN) {
                     const bool last_tile = c0 + BN >= y_end;
                     mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
                     for (int kc = 0; kc < P.kchunks; ++kc) {
+                        const bool streamed = kc >= P.resident;
+                        const int y_stage = stage;
                         mbar_wait(&full_bar[stage], phase);
+                        if (++stage == P.stages) { stage = 0; phase ^= 1; }
+                        const int q_stage = stage;
+                        if (streamed) {
+                            mbar_wait(&full_bar[stage], phase);
+                            if (++stage == P.stages) { stage = 0; phase ^= 1; }
+                        }
                         tc_fence_after();
                         if (elect_one()) {
-                            const uint64_t d_q = make_smem_desc<Cfg>(q_u32 + (uint32_t)kc * Cfg::A_BYTES);
-                            const uint64_t d_y = make_smem_desc<Cfg>(stage_u32 + (uint32_t)stage * Cfg::B_BYTES);
+                            const uint64_t d_q = make_smem_desc<Cfg>(
+                                streamed ? stage_u32 + (uint32_t)q_stage * Cfg::B_BYTES
+                                         : q_u32 + (uint32_t)kc * Cfg::A_BYTES);
+                            const uint64_t d_y = make_smem_desc<Cfg>(stage_u32 + (uint32_t)y_stage * Cfg::B_BYTES);
 #pragma unroll
                             for (int k = 0; k < BK / UMMA_K; ++k)
                                 umma_tf32_pair(tmem_d, d_q + 2 * k, d_y + 2 * k, idesc, (kc | k) != 0);
-                            umma_commit_pair(empty_u32 + (uint32_t)stage * 8, 0x3);
+                            umma_commit_pair(empty_u32 + (uint32_t)y_stage * 8, 0x3);
+                            if (streamed) umma_commit_pair(empty_u32 + (uint32_t)q_stage * 8, 0x3);
                             if (kc == P.kchunks - 1) {
                                 umma_commit_pair(smem_u32(&tmem_full[acc]), 0x3);
-                                if (last_tile) umma_commit_pair(smem_u32(q_empty), 0x3);
+                                if (last_tile && P.resident > 0) umma_commit_pair(smem_u32(q_empty), 0x3);
                             }
                         }
                         __syncwarp();
-                        if (++stage == P.stages) { stage = 0; phase ^= 1; }
                     }
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
@@ -234,7 +250,6 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap map_q,
         }
     }
     } else {
-    if constexpr (DUAL && DUAL_REGS) asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     if (warp < 4) {
         // ------------------------------------------------------ row epilogue, both CTAs
         const int lrow = warp * 32 + lane;
@@ -295,7 +310,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap map_q,
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
-                epilogue_tile<BN, !DUAL || DUAL_REGS>(L, lrow, yk, taddr, c0, tau, cnt, lane);
+                epilogue_tile<BN, !DUAL>(L, lrow, yk, taddr, c0, tau, cnt, lane);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(tmem_empty_leader + (uint32_t)acc * 8);
@@ -352,7 +367,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap map_q,
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-                column_tile<BN, DUAL_REGS>(FP, Q, tk, taddr, c0, xk, row_base, lane);
+                column_tile<BN>(FP, Q, tk, taddr, c0, xk, row_base, lane);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(tmem_empty_leader + (uint32_t)acc * 8);
@@ -381,20 +396,39 @@ static size_t screen_fixed_smem(int cap, int slots, bool dual) {
            lists_bytes(BM, cap, slots) + (2 * MAX_STAGES + 6) * 8 + 16;
 }
 
-// Stages the shape gets (0: the screen kernel does not take it), choosing the append-buffer size.
-static int screen_config(int dpad, int cap, bool dual, int max_smem, int *slots_out) {
-    if (dpad <= 0 || dpad % S_BK != 0 || dpad > S_MAX_DPAD || cap <= 0 || cap > 64) return 0;
-    const size_t q_bytes = (size_t)BM * dpad * 4;
-    const size_t stage = (size_t)S_HALF * S_BK * 4;
-    auto stages_for = [&](int slots) {
-        const size_t fixed = q_bytes + screen_fixed_smem(cap, slots, dual) + 1024;
+// Ring slots the shape gets (0: the screen kernel does not take it), choosing the append-buffer
+// size and how many K chunks of the query tile stay resident.  Shared memory left by the lists
+// is cut into 16 KB units; at least SCREEN_MIN_STAGES of them form the ring, the rest hold
+// query chunks.  A fully resident tile gets the remaining units as extra ring slots.
+constexpr int SCREEN_MIN_STAGES = 4;
+static int screen_config(int dpad, int cap, bool dual, int max_smem, int *slots_out,
+                         int *resident_out = nullptr) {
+    if (dpad <= 0 || dpad % S_BK != 0 || dpad > S_MAX_DPAD || cap <= 0 || cap > 128) return 0;
+    const int kchunks = dpad / S_BK;
+    const size_t unit = (size_t)S_HALF * S_BK * 4;
+    auto units_for = [&](int slots) {
+        const size_t fixed = screen_fixed_smem(cap, slots, dual) + 1024;
         if (fixed >= (size_t)max_smem) return 0;
-        return (int)min((size_t)MAX_STAGES, ((size_t)max_smem - fixed) / stage);
+        return (int)(((size_t)max_smem - fixed) / unit);
     };
+    // longer append buffers mean fewer list merges, but every 16 KB they cost is a resident
+    // query chunk less: shrink them while that buys residency (or the minimum ring)
     int slots = lists_buffer_slots(cap);
-    while (slots > LISTS_MIN_SLOTS && stages_for(slots) < 4) slots -= LISTS_GROUP;
-    const int stages = stages_for(slots);
+    for (int cand = slots - LISTS_GROUP; cand >= LISTS_MIN_SLOTS; cand -= LISTS_GROUP)
+        if (min(kchunks + SCREEN_MIN_STAGES, units_for(cand)) >
+            min(kchunks + SCREEN_MIN_STAGES, units_for(slots)))
+            slots = cand;
+    const int units = units_for(slots);
+    int resident = min(kchunks, units - SCREEN_MIN_STAGES);
+    if (resident < 0) resident = 0;
+    if (const char *env = getenv("KB2_SCREEN_RESIDENT")) {
+        const int r = atoi(env);
+        if (r >= 0 && r < resident) resident = r;
+    }
+    const int stages = min(MAX_STAGES, units - resident);
     if (slots_out) *slots_out = slots;
+    if (resident_out) *resident_out = resident;
+    // a streamed chunk occupies two slots: never run with fewer than 3
     return stages >= 3 ? stages : 0;
 }
 
@@ -404,7 +438,7 @@ static int launch_screen(ScreenParams P, const FusedParams &FP, const float *q_h
     CUtensorMap mq, my;
     if (make_map(&mq, q_hi, P.nq, dpad, BM, S_BK)) return 1;
     if (make_map(&my, y_hi, P.ny, dpad, S_HALF, S_BK)) return 1;
-    const size_t need = (size_t)BM * dpad * 4 + (size_t)P.stages * S_HALF * S_BK * 4 +
+    const size_t need = (size_t)(P.resident + P.stages) * S_HALF * S_BK * 4 +
                         screen_fixed_smem(P.cap, P.buf_slots, DUAL);
     const size_t smem = min((size_t)max_smem, need + 1024);
     KB2_CUDA(cudaFuncSetAttribute(knn_screen_kernel<DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -428,6 +462,17 @@ extern "C" int kb2_screen_stages(int dpad, int cap, int dual) {
     if (cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
         return 0;
     return screen_config(dpad, cap, dual != 0, max_smem, nullptr);
+}
+
+extern "C" int kb2_screen_config(int dpad, int cap, int dual, int max_smem, int *slots,
+                                 int *resident) {
+    if (max_smem <= 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+        if (cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+            return 0;
+    }
+    return screen_config(dpad, cap, dual != 0, max_smem, slots, resident);
 }
 
 extern "C" int kb2_screen_plan(int64_t nq, int64_t ny, int dpad, int cap, int sm_count,
@@ -481,12 +526,12 @@ extern "C" int kb2_knn_screen(const float *q_hi, const float *q_key, int64_t nq,
     P.per_step = ceil_div64(ceil_div64(ny, steps), S_BN) * S_BN;
     P.q_tiles = ceil_div64(nq, BM); P.y_key = y_key; P.cand_idx = cand_idx; P.cand_key = cand_key;
     P.chain_flag = chain_flag;
-    P.stages = screen_config(dpad, cap, dual, max_smem, &P.buf_slots);
-    KB2_CHECK(P.stages > 0, "knn_screen: dpad=%d cap=%d does not fit the resident-query kernel "
-              "(dpad <= %d, multiple of %d; see kb2_screen_stages)", dpad, cap, S_MAX_DPAD, S_BK);
+    P.stages = screen_config(dpad, cap, dual, max_smem, &P.buf_slots, &P.resident);
+    KB2_CHECK(P.stages > 0, "knn_screen: dpad=%d cap=%d is not supported (dpad <= %d, multiple of "
+              "%d, cap <= 128; see kb2_screen_stages)", dpad, cap, S_MAX_DPAD, S_BK);
     if (const char *env = getenv("KB2_SCREEN_STAGES")) {
         const int s = atoi(env);
-        if (s >= 2 && s <= P.stages) P.stages = s;
+        if (s >= 3 && s <= P.stages) P.stages = s;
     }
     FusedParams FP;
     FP.x_key = q_key; FP.tau_col = tau_col; FP.col_cnt = col_cnt;

@@ -44,6 +44,22 @@ def _device_of(algo):
     return dev if dev is not None else torch.device("cuda", torch.cuda.current_device())
 
 
+def _to_host(*tensors):
+    """Device results -> numpy.  Large results go through page-locked buffers from torch's
+    caching host allocator (one DMA each, no staging through the driver's bounce buffer; the
+    first call pays the cudaHostAlloc, later calls reuse the cached blocks) and the returned
+    arrays are views of those buffers."""
+    if sum(t.numel() * t.element_size() for t in tensors) < (8 << 20):
+        return tuple(t.cpu().numpy() for t in tensors)
+    outs = []
+    for t in tensors:
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t, non_blocking=True)
+        outs.append(h)
+    torch.cuda.current_stream(tensors[0].device).synchronize()
+    return tuple(h.numpy() for h in outs)
+
+
 def _rows_on_device(algo, data, cache):
     """fp32 rows of an embedding matrix on the device (re-uses the backend's upload)."""
     if hasattr(algo, "_prepare"):
@@ -140,9 +156,7 @@ class HubnessReduction(ABC):
                     getattr(self.nn_algo, "distributed", False) and \
                     torch.distributed.get_rank() != 0:
                 return dist, ind
-            # (pinned staging buffers were tried: the first-call cudaHostAlloc costs more than the
-            # pageable copy of an (n, k) result saves)
-            return dist.cpu().numpy(), ind.cpu().numpy()
+            return _to_host(dist, ind)
         return dist, ind
 
     def kneighbors(self, k: Optional[int] = None):

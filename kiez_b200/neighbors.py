@@ -147,26 +147,83 @@ _METRIC_CODES = {
 }
 
 
+class _PendingRows:
+    """Bookkeeping of a matrix whose rows are still being uploaded (kiez_b200/upload.py): the
+    first `done` chunks are on the device AND prepared."""
+
+    __slots__ = ("algo", "upload", "done")
+
+    def __init__(self, algo, upload):
+        self.algo, self.upload, self.done = algo, upload, 0
+
+
 class PreparedRows:
     """Device-resident operands of one embedding matrix: the raw fp32 rows (exact
-    finish), their 3xTF32 split and selection term (candidate search)."""
+    finish), their 3xTF32 split and selection term (candidate search).
 
-    __slots__ = ("raw", "hi", "lo", "key", "sqnorm", "keymax", "err", "errmax", "n", "d", "dpad",
-                 "base", "_owner")
+    A matrix that arrives from the host is prepared chunk by chunk as its upload proceeds:
+    `ensure(upto)` makes the first `upto` rows usable on the current stream (all rows when
+    omitted); `rows(lo, hi)` does so for the shard it returns, `take` / `keymax` / `errmax`
+    for the whole matrix.  Every consumer that reads the full tensors calls `ensure()` first."""
+
+    __slots__ = ("raw", "hi", "lo", "key", "sqnorm", "_keymax", "err", "_errmax", "n", "d", "dpad",
+                 "base", "_owner", "_pending", "_root", "presample")
 
     def __init__(self, raw, hi, lo, key, sqnorm, base=0, owner=None, keymax=None, err=None,
-                 errmax=None):
+                 errmax=None, root=None):
         self.raw, self.hi, self.lo, self.key, self.sqnorm = raw, hi, lo, key, sqnorm
-        self.keymax = keymax    # device scalar >= max(key): input of the screen's completeness proof
+        self._keymax = keymax   # device scalar >= max(key): input of the screen's completeness proof
         # TF32 rounding error of the rows: err [n] >= ||w - hi||^2, errmax (device scalar) its maximum
-        self.err, self.errmax = err, errmax
+        self.err, self._errmax = err, errmax
         self.n, self.d = raw.shape
         self.dpad = hi.shape[1]
         self.base = base        # global id of row 0 (multi-GPU shards)
         self._owner = owner     # keeps the user's array alive while its id() is a cache key
+        self._pending = None    # _PendingRows while the upload / preparation is in progress
+        self._root = root       # the matrix this is a shard of (its maxima cover the shard)
+        self.presample = None   # ((count, step), PreparedRows) of a strided row sample uploaded first
+
+    def ensure(self, upto=None):
+        """Rows [0, upto) (default: all) are uploaded and prepared once the work enqueued on the
+        current stream so far has run."""
+        if self._root is not None:
+            # a shard: its parent prepares a prefix of chunks covering it
+            self._root.ensure(None if upto is None else self._root_offset() + upto)
+            return self
+        p = self._pending
+        if p is None:
+            return self
+        up = p.upload
+        last = len(up.bounds) - 1 if upto is None else up.chunk_of(max(0, min(self.n, upto) - 1))
+        stream = torch.cuda.current_stream(self.raw.device)
+        while p.done <= last:
+            up.wait(p.done, stream)
+            lo, hi = up.bounds[p.done]
+            p.algo._prepare_range(self, lo, hi)
+            p.done += 1
+        if p.done == len(up.bounds):
+            self._pending = None
+            p.algo._finish_maxima(self)
+        return self
+
+    def _root_offset(self):
+        return self.base - self._root.base
+
+    @property
+    def keymax(self):
+        root = self._root if self._root is not None else self
+        root.ensure()
+        return root._keymax
+
+    @property
+    def errmax(self):
+        root = self._root if self._root is not None else self
+        root.ensure()
+        return root._errmax
 
     def take(self, idx):
         """The rows `idx` (a device int64 tensor) gathered into a new contiguous set."""
+        self.ensure()
         return PreparedRows(self.raw.index_select(0, idx), self.hi.index_select(0, idx),
                             self.lo.index_select(0, idx), self.key.index_select(0, idx),
                             None if self.sqnorm is None else self.sqnorm.index_select(0, idx),
@@ -176,10 +233,12 @@ class PreparedRows:
 
     def rows(self, lo, hi):
         """A contiguous row shard (views, no copy)."""
+        self.ensure(hi)
+        root = self._root if self._root is not None else self
         return PreparedRows(self.raw[lo:hi], self.hi[lo:hi], self.lo[lo:hi], self.key[lo:hi],
                             None if self.sqnorm is None else self.sqnorm[lo:hi],
-                            base=self.base + lo, owner=self._owner, keymax=self.keymax,
-                            err=None if self.err is None else self.err[lo:hi], errmax=self.errmax)
+                            base=self.base + lo, owner=self._owner,
+                            err=None if self.err is None else self.err[lo:hi], root=root)
 
 
 def candidate_capacity(c: int) -> int:
@@ -264,13 +323,56 @@ class B200Mixin:
         self._screen_ok = None
         self._screen_boost = False
         self._input_is_numpy = isinstance(source, np.ndarray)
+        self._start_uploads(source, target, only_fit_target)
         return super().fit(source, target, only_fit_target=only_fit_target)
 
     def _fit(self, data, is_source: bool):
-        return self._prepare(data, cache=True)
+        return self._prepare(data, cache=True, lazy=True)
+
+    # Host inputs (what kiez passes): upload on a background thread in row chunks, overlapped
+    # with the searches (kiez_b200/upload.py).  Order: the target first -- the first launches of
+    # the reverse / dual-direction pass need all of it --, then the strided row sample of the
+    # source that seeds the column thresholds, then the source, whose row segments the pass
+    # consumes in order.  KB2_ASYNC_UPLOAD=0 restores the plain synchronous copies.
+    ASYNC_UPLOAD_MIN_BYTES = 8 << 20
+
+    def _start_uploads(self, source, target, only_fit_target):
+        from . import upload
+
+        self._uploader = None
+        self._pending_uploads = {}
+        if self.distributed or os.environ.get("KB2_ASYNC_UPLOAD", "1") == "0":
+            return
+        mats = [m for m in ((target, source) if not only_fit_target else (target,))
+                if m is not None and upload.eligible(m)
+                and m.shape[0] * m.shape[1] * 4 >= self.ASYNC_UPLOAD_MIN_BYTES]
+        if not mats or (source is not None and target is not None
+                        and tuple(source.shape[1:]) != tuple(target.shape[1:])):
+            return
+        cosine = self._metric_code == self._lib.METRIC_COSINE
+        first = source if not only_fit_target else target      # the matrix that defines the centre
+        if self.center and not cosine and upload.eligible(first):
+            # any vector near the mean serves (distances are translation invariant): the mean
+            # of a strided row sample, so that no pass over the whole host matrix is needed
+            host = first if isinstance(first, np.ndarray) else first.numpy()
+            stride = max(1, host.shape[0] // 65536)
+            self._center_vec = torch.from_numpy(
+                host[::stride].mean(axis=0, dtype=np.float64).astype(np.float32)).to(self.device)
+        up = upload.Uploader()
+        with torch.cuda.device(self.device):
+            for m in mats:
+                if m is source and target is not None and not only_fit_target:
+                    cap = candidate_capacity(self.n_candidates)
+                    n_s = self._fused_sample_rows(m.shape[0], cap)
+                    step = max(1, m.shape[0] // n_s)
+                    self._pending_uploads[("sample", id(m))] = (
+                        (n_s, step), up.add(upload.HostUpload(m, self.device, rows=(n_s, step))))
+                self._pending_uploads[id(m)] = up.add(upload.HostUpload(m, self.device))
+        up.start()
+        self._uploader = up
 
     def _kneighbors(self, k, query, index, return_distance, is_self_querying):
-        q = self._prepare(query, cache=False)
+        q = self._prepare(query, cache=False, lazy=True)
         if is_self_querying and k > index.n - 1:
             # sklearn raises for n_neighbors > n_samples_fit - 1 with X=None
             raise ValueError(
@@ -339,44 +441,94 @@ class B200Mixin:
 
         return upload_sharded(data, self.device)
 
-    def _prepare(self, data, cache: bool) -> PreparedRows:
+    def _prepare(self, data, cache: bool, lazy: bool = False) -> PreparedRows:
+        """The prepared operands of `data` (cached per fitted matrix).  `lazy`: a matrix whose
+        upload is still in progress is returned as it is -- the caller `ensure`s the rows it
+        reads; otherwise every row is usable on return."""
         hit = self._prepared.get(id(data))
         if hit is not None:
-            return hit
+            return hit if lazy else hit.ensure()
         lib = self._lib
-        raw = self.to_device(data)
+        pending = getattr(self, "_pending_uploads", {}).pop(id(data), None)
+        raw = pending.dev if pending is not None else self.to_device(data)
         if raw.dim() != 2:
             raise ValueError(f"Expected a 2-d embedding matrix, got shape {tuple(raw.shape)}")
         n, d = raw.shape
         cosine = self._metric_code == lib.METRIC_COSINE
         if self._center_vec is None and self.center and not cosine and n > 0:
             # distances are translation invariant; centring keeps ||y||^2 - 2 q.y well
-            # conditioned in fp32 for embeddings far from the origin
-            self._center_vec = raw.mean(dim=0).to(torch.float32).contiguous()
+            # conditioned in fp32 for embeddings far from the origin.  Any vector near the mean
+            # serves: the mean of a strided row sample (65536 to 131071 rows of a large matrix)
+            stride = max(1, n // 65536)
+            self._center_vec = raw[::stride].mean(dim=0, dtype=torch.float64).to(torch.float32).contiguous()
         dpad = lib.lib.kb2_padded_dim(d)
-        raw32 = raw if raw.dtype == torch.float32 else raw.to(torch.float32)
         with torch.cuda.device(self.device):
             hi = torch.empty((n, dpad), dtype=torch.float32, device=self.device)
             lo = torch.empty((n, dpad), dtype=torch.float32, device=self.device)
             key = torch.empty((n,), dtype=torch.float32, device=self.device)
             sqn = torch.empty((n,), dtype=torch.float64, device=self.device) if cosine else None
-            if n:
-                lib.call("kb2_prepare_rows", lib.ptr(raw32), n, d, raw32.stride(0),
-                         None if cosine else lib.ptr(self._center_vec), self._metric_code,
-                         lib.ptr(hi), lib.ptr(lo), dpad, lib.ptr(key), lib.ptr(sqn),
-                         lib.stream_ptr())
-                if cosine and raw.dtype == torch.float64:
-                    sqn = (raw * raw).sum(dim=1)      # exact norms of the float64 rows
-            keymax = torch.empty((1,), dtype=torch.float32, device=self.device)
-            lib.call("kb2_max_f32", lib.ptr(key), n, lib.ptr(keymax), lib.stream_ptr())
             err = torch.empty((n,), dtype=torch.float32, device=self.device)
+            keymax = torch.empty((1,), dtype=torch.float32, device=self.device)
             errmax = torch.empty((1,), dtype=torch.float32, device=self.device)
-            lib.call("kb2_split_error_terms", lib.ptr(lo), n, dpad, lib.ptr(err), lib.ptr(errmax),
-                     lib.stream_ptr())
         prep = PreparedRows(raw, hi, lo, key, sqn, owner=data, keymax=keymax, err=err, errmax=errmax)
+        if pending is not None:
+            prep._pending = _PendingRows(self, pending)
+            sample = getattr(self, "_pending_uploads", {}).pop(("sample", id(data)), None)
+            if sample is not None:
+                prep.presample = (sample[0], self._prepare_upload(sample[1], owner=data))
+            if not lazy:
+                prep.ensure()
+        else:
+            if n:
+                self._prepare_range(prep, 0, n)
+                if cosine and raw.dtype == torch.float64:
+                    prep.sqnorm = (raw * raw).sum(dim=1)      # exact norms of the float64 rows
+            self._finish_maxima(prep)
         if cache:
             self._prepared[id(data)] = prep
         return prep
+
+    def _prepare_upload(self, up, owner) -> PreparedRows:
+        """PreparedRows over the device buffer of an upload in progress (prepared lazily)."""
+        n, d = up.dev.shape
+        dpad = self._lib.lib.kb2_padded_dim(d)
+        cosine = self._metric_code == self._lib.METRIC_COSINE
+        dev = self.device
+        with torch.cuda.device(dev):
+            prep = PreparedRows(up.dev, torch.empty((n, dpad), dtype=torch.float32, device=dev),
+                                torch.empty((n, dpad), dtype=torch.float32, device=dev),
+                                torch.empty((n,), dtype=torch.float32, device=dev),
+                                torch.empty((n,), dtype=torch.float64, device=dev) if cosine else None,
+                                owner=owner,
+                                keymax=torch.empty((1,), dtype=torch.float32, device=dev),
+                                err=torch.empty((n,), dtype=torch.float32, device=dev),
+                                errmax=torch.empty((1,), dtype=torch.float32, device=dev))
+        prep._pending = _PendingRows(self, up)
+        return prep
+
+    def _prepare_range(self, prep: PreparedRows, lo: int, hi: int) -> None:
+        """kb2_prepare_rows + kb2_split_error_terms for rows [lo, hi) of `prep` (the index
+        build, chunk by chunk while a host matrix is still arriving)."""
+        lib = self._lib
+        raw = prep.raw
+        raw32 = raw[lo:hi] if raw.dtype == torch.float32 else raw[lo:hi].to(torch.float32)
+        cosine = self._metric_code == lib.METRIC_COSINE
+        with torch.cuda.device(self.device):
+            scratch = torch.empty((1,), dtype=torch.float32, device=self.device)
+            lib.call("kb2_prepare_rows", lib.ptr(raw32), hi - lo, prep.d, raw32.stride(0),
+                     None if cosine else lib.ptr(self._center_vec), self._metric_code,
+                     lib.ptr(prep.hi[lo:hi]), lib.ptr(prep.lo[lo:hi]), prep.dpad,
+                     lib.ptr(prep.key[lo:hi]),
+                     None if prep.sqnorm is None else lib.ptr(prep.sqnorm[lo:hi]), lib.stream_ptr())
+            lib.call("kb2_split_error_terms", lib.ptr(prep.lo[lo:hi]), hi - lo, prep.dpad,
+                     lib.ptr(prep.err[lo:hi]), lib.ptr(scratch), lib.stream_ptr())
+
+    def _finish_maxima(self, prep: PreparedRows) -> None:
+        """max ||w||^2 and max ||w - hi||^2 over all rows: inputs of the completeness proof."""
+        lib = self._lib
+        with torch.cuda.device(self.device):
+            lib.call("kb2_max_f32", lib.ptr(prep.key), prep.n, lib.ptr(prep._keymax), lib.stream_ptr())
+            lib.call("kb2_max_f32", lib.ptr(prep.err), prep.n, lib.ptr(prep._errmax), lib.stream_ptr())
 
     # -- screen (1xTF32 proposals + completeness proof) ------------------------------
     def _use_screen(self, q: PreparedRows, y: PreparedRows, cap: int, dual: bool) -> bool:
@@ -588,10 +740,15 @@ class B200Mixin:
             sm = torch.cuda.get_device_properties(dev).multi_processor_count
             screen = self._use_screen(rows, cols, cap, dual=True)
             prof = getattr(self, "_profile", None)       # bench.py: CUDA events around the searches
-            # 1. column thresholds from a strided sample of the rows
+            cols.ensure()
+            # 1. column thresholds from a strided sample of the rows (a host matrix still being
+            #    uploaded sent exactly these rows ahead, see _start_uploads)
             n_s = self._fused_sample_rows(rows.n, cap)
             step = max(1, rows.n // n_s)
-            sample = rows.take(torch.arange(n_s, device=dev, dtype=torch.int64) * step)
+            if rows.presample is not None and rows.presample[0] == (n_s, step):
+                sample = rows.presample[1].ensure()
+            else:
+                sample = rows.take(torch.arange(n_s, device=dev, dtype=torch.int64) * step)
             if screen and self._use_screen(cols, sample, cap, dual=False):
                 _s_idx, s_key, lists = self._screen_search(cols, sample, cap)
             else:
@@ -663,6 +820,7 @@ class B200Mixin:
                              cap, lib.ptr(tau), st)
                     if emitted is not None:
                         emitted -= torch.where(col_cnt < (1 << 30), col_cnt, 0).sum()
+            rows.ensure()
             if screen:
                 self.search_stats["screen_rows"] += rows.n
                 bad_rows = torch.nonzero(unv_rows).flatten()
@@ -731,6 +889,8 @@ class B200Mixin:
         lib = self._lib
         if q.d != y.d:
             raise ValueError(f"query has {q.d} features, index has {y.d}")
+        q.ensure()
+        y.ensure()
         cap = min(self._capacity(k, q), lib.lib.kb2_max_candidates())
         if k > cap:
             raise ValueError(
@@ -775,6 +935,8 @@ class B200Mixin:
         """The 3xTF32 search (knn_tc2.cu / knn_tc.cu / the SIMT cross-check) + exact finish."""
         lib = self._lib
         dev = self.device
+        q.ensure()
+        y.ensure()
         with torch.cuda.device(dev):
             out_d = torch.empty((q.n, k), dtype=torch.float64, device=dev)
             out_i = torch.empty((q.n, k), dtype=torch.int64, device=dev)

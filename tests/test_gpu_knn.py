@@ -52,6 +52,9 @@ SHAPES = [
     (300, 1000, 64, 50),
     (513, 2049, 128, 100),   # c = 100 (config C3's candidate count)
     (1000, 5000, 256, 10),
+    (600, 3000, 256, 50),    # c = 50 at d = 256 (C2 / C4-c50): partially resident query tile
+    (400, 2500, 256, 100),   # c = 100 at d = 256 (C3): 2 of 8 K chunks resident
+    (300, 900, 600, 10),     # dpad = 608 > 256: most of the query tile is streamed
 ]
 
 
@@ -298,22 +301,72 @@ def test_screen_chained_ranges(monkeypatch, fused):
     assert algo.search_stats["screen_unverified"] < 0.05 * algo.search_stats["screen_rows"]
 
 
-def test_screen_not_taken_for_float64_or_wide_rows():
-    """float64 callers and d > 256 keep the 3xTF32 search (the proof assumes fp32 operands; the
-    resident query tile needs d <= 256)."""
+def test_screen_not_taken_for_float64_but_for_wide_rows():
+    """float64 callers keep the 3xTF32 search (the proof assumes fp32 operands).  Rows wider than
+    the 256 features a resident query tile can hold take the screen with a partially resident
+    tile; beyond dpad = 1024 the 3xTF32 search takes over."""
     rng = np.random.default_rng(3)
     algo = _algo(n_candidates=5, impl="screen")
     algo.fit(rng.standard_normal((200, 20)), rng.standard_normal((300, 20)))   # float64
     algo.kneighbors(k=5)
     assert algo.search_stats["screen_rows"] == 0
-    q, y = _data(200, 400, 300, seed=4)
-    algo = _algo(n_candidates=5, impl="screen")
-    algo.fit(q, y)
-    dist, ind = algo.kneighbors(k=5)
-    assert algo.search_stats["screen_rows"] == 0
-    want_d, want_i = O.knn_brute(q.astype(np.float64), y.astype(np.float64), 5, "euclidean")
-    O.assert_neighbors_match(dist.cpu().numpy(), ind.cpu().numpy(), want_d, want_i, RTOL, ATOL,
-                             what="wide rows")
+    for d, screened in ((300, 200), (1100, 0)):
+        q, y = _data(200, 400, d, seed=4)
+        algo = _algo(n_candidates=5, impl="screen")
+        algo.fit(q, y)
+        dist, ind = algo.kneighbors(k=5)
+        assert algo.search_stats["screen_rows"] == screened
+        want_d, want_i = O.knn_brute(q.astype(np.float64), y.astype(np.float64), 5, "euclidean")
+        O.assert_neighbors_match(dist.cpu().numpy(), ind.cpu().numpy(), want_d, want_i, RTOL, ATOL,
+                                 what=f"wide rows d={d}")
+
+
+def test_screen_partial_residency_plan():
+    """kb2_screen_config: how the kernel divides shared memory between the resident part of the
+    query tile and the ring, for the BASELINE.json shapes."""
+    import ctypes as C
+
+    from kiez_b200 import _lib
+
+    def plan(dpad, cap, dual):
+        slots, res = C.c_int(0), C.c_int(0)
+        stages = _lib.lib.kb2_screen_config(dpad, cap, dual, 0, C.addressof(slots), C.addressof(res))
+        return stages, slots.value, res.value
+
+    assert plan(256, 16, 1)[2] == 8 and plan(256, 16, 1)[0] >= 4       # C4: fully resident
+    st, _sl, res = plan(256, 56, 0)                                     # C2 / C4 at c = 50
+    assert st >= 4 and 4 <= res < 8
+    st, _sl, res = plan(256, 112, 0)                                    # C3
+    assert st >= 4 and 1 <= res < 8
+    assert plan(128, 56, 0)[2] == 4                                     # C5: fully resident
+    assert plan(2048, 16, 0)[0] == 0 and plan(256, 136, 0)[0] == 0
+
+
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("resident", [None, 0, 3])
+def test_screen_streamed_query_chunks(monkeypatch, fused, resident):
+    """The ring carries query chunks next to the index tiles (KB2_SCREEN_RESIDENT forces fewer
+    resident chunks than fit): same results as the oracle, chained ranges included."""
+    if resident is not None:
+        monkeypatch.setenv("KB2_SCREEN_RESIDENT", str(resident))
+    monkeypatch.setenv("KB2_SCREEN_RANGE_MB", "1")
+    nq, ny, d, c = 39000, 5000, 256, 50
+    q, y = _data(nq, ny, d, seed=41)
+    algo = _algo(n_candidates=c, impl="screen", fused=fused)
+    qp, yp = algo._prepare(q, cache=False), algo._prepare(y, cache=False)
+    rows = np.random.default_rng(1).choice(nq, 200, replace=False)
+    if fused:
+        (fd, fi), (rd, ri) = algo.search_both(qp, yp, c, c)
+        cols = np.random.default_rng(2).choice(ny, 100, replace=False)
+        want_d, want_i = O.knn_brute(y[cols].astype(np.float64), q.astype(np.float64), c, "euclidean")
+        O.assert_neighbors_match(rd[cols].cpu().numpy(), ri[cols].cpu().numpy(), want_d, want_i,
+                                 RTOL, ATOL, what="streamed rev")
+    else:
+        fd, fi = algo.search(qp, yp, c)
+    assert algo.search_stats["screen_rows"] == (nq + ny if fused else nq)
+    want_d, want_i = O.knn_brute(q[rows].astype(np.float64), y.astype(np.float64), c, "euclidean")
+    O.assert_neighbors_match(fd[rows].cpu().numpy(), fi[rows].cpu().numpy(), want_d, want_i,
+                             RTOL, ATOL, what="streamed fwd")
 
 
 def _tight_clusters(n, d, seed, noise=0.02):
