@@ -64,9 +64,9 @@ def parse_args():
                          "re-search of unproven rows (same results)")
     ap.add_argument("--data", default="gaussian", choices=["gaussian", "hubby"],
                     help="synthetic distribution (see synth)")
-    ap.add_argument("--shard-grid", default=None,
-                    help="EXPERIMENTAL, N>1: RxC grid of ranks for the dual-direction pass "
-                         "(default: column shards)")
+    ap.add_argument("--shard-mode", default="rows", choices=["rows", "cols"],
+                    help="N>1, dual-direction pass: shard the source rows (thresholds agreed across "
+                         "ranks; default) or the target columns")
     ap.add_argument("--no-hub-scores", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -100,9 +100,9 @@ def make_config(args, w, world):
     return {"workload": w["name"], "l2": "inputs (>=1 GB) exceed the 126 MB L2",
             "search_impl": args.search_impl, "fused": args.fused, "precision": args.precision,
             "hub_scores": not args.no_hub_scores,
-            "parallelism": (f"rows sharded over {world} GPU(s)"
-                            + (f" as a {args.shard_grid} rows x columns grid" if args.shard_grid else "")
-                            + ", NCCL exchange + merge kernel") if world > 1 else "single GPU"}
+            "parallelism": (f"{'source rows' if args.shard_mode == 'rows' else 'target columns'} "
+                            f"sharded over {world} GPU(s), NCCL exchange + merge kernels")
+            if world > 1 else "single GPU"}
 
 
 def synth(n, d, seed, device, data="gaussian"):
@@ -465,8 +465,7 @@ def run_b200(args, w):
     def make():
         algo = B200(n_candidates=w["c"], metric="euclidean", impl=args.search_impl,
                     distributed=world > 1, precision=args.precision,
-                    shard_grid=(tuple(int(v) for v in args.shard_grid.lower().split("x"))
-                                if args.shard_grid and world > 1 else None),
+                    shard_mode=args.shard_mode,
                     fused={"auto": "auto", "on": True, "off": False}[args.fused])
         algo.host_result = "rank0"          # numpy callers: only rank 0 downloads the result
         return Kiez(n_candidates=w["c"], algorithm=algo, hubness=w["hubness"],

@@ -125,6 +125,21 @@ int kb2_col_select(const uint64_t *col_buf, const uint32_t *col_cnt, int64_t ny,
  * column with more than col_cap emitted rows keeps a sticky overflow count. */
 int kb2_col_compact(uint64_t *col_buf, uint32_t *col_cnt, int64_t ny, int col_cap, int cap,
                     float *tau_col, void *stream);
+/* Multi-GPU form of the same stage (reverse kNN of hubness_reduction/base.py:37-42 with the
+ * SOURCE rows sharded over the ranks): every rank runs the dual-direction
+ * pass over its own rows, so the per-column state has to agree across ranks.
+ * kb2_col_heads: the first min(count, cap) entries of every column buffer (after
+ *   kb2_col_compact: the best cap so far), EMPTY-padded -> out_entries [ny][cap] packed
+ *   (key bits << 32 | row + row_offset) and / or out_keys [ny][cap] fp32 (+inf padded); either
+ *   may be NULL.  The keys are all-gathered between row segments, the entries exchanged with an
+ *   all-to-all after the last one (each rank finishes a shard of the columns).
+ * kb2_kth_key: tau[col] = min(tau[col], kth smallest of keys[p * part_stride + col * L + j],
+ *   p < nparts, j < L): the threshold every rank continues with (nparts * L <= 1024). */
+int kb2_col_heads(const uint64_t *col_buf, const uint32_t *col_cnt, int64_t ny, int col_cap,
+                  int cap, int64_t row_offset, uint64_t *out_entries, float *out_keys,
+                  void *stream);
+int kb2_kth_key(const float *keys, int nparts, int64_t part_stride, int64_t ny, int L, int kth,
+                float *tau, void *stream);
 
 /*
  * Screening candidate search (knn_screen.cu): the same stage of the reference as

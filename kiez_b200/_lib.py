@@ -17,6 +17,8 @@ LIB_PATH = os.environ.get("KB2_LIB") or os.path.join(_HERE, "lib", "libkiez_b200
 METRIC_EUCLIDEAN, METRIC_SQEUCLIDEAN, METRIC_COSINE = 0, 1, 2
 RESCALE_CSLS, RESCALE_LS, RESCALE_NICDM, RESCALE_MP_GAUSS = 0, 1, 2, 3
 KNN_AUTO, KNN_TC, KNN_SIMT, KNN_TC1 = 0, 1, 2, 3
+#: select.cuh EMPTY_ENTRY (key +inf, id -1) as a signed 64-bit value: pads packed candidate entries
+EMPTY_ENTRY = 0xFF800000FFFFFFFF - (1 << 64)
 
 _p = C.c_void_p
 _i64 = C.c_int64
@@ -35,6 +37,8 @@ SIGNATURES = {
                       _p, _p],
     "kb2_col_select": [_p, _p, _i64, _int, _int, _p, _p, _p, _p, _p],
     "kb2_col_compact": [_p, _p, _i64, _int, _int, _p, _p],
+    "kb2_col_heads": [_p, _p, _i64, _int, _int, _i64, _p, _p, _p],
+    "kb2_kth_key": [_p, _int, _i64, _i64, _int, _int, _p, _p],
     "kb2_screen_stages": [_int, _int, _int],
     "kb2_screen_config": [_int, _int, _int, _int, _p, _p],
     "kb2_screen_plan": [_i64, _i64, _int, _int, _int, _p, _p],

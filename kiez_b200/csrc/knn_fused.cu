@@ -341,6 +341,60 @@ col_select_kernel(ent_t *__restrict__ col_buf, unsigned int *__restrict__ col_cn
     }
 }
 
+// Multi-GPU exchanges of the row-sharded dual-direction pass (kiez_b200/distributed.py): every
+// rank sees only its own rows, so the per-column state that must agree across ranks -- the
+// thresholds between row segments, the best rows at the end -- travels as the HEAD of each
+// column buffer: its first min(count, cap) entries (after kb2_col_compact: the best cap so far),
+// padded with EMPTY_ENTRY.  out_ent: packed entries with row ids made global (+ row_offset);
+// out_key: their fp32 keys (+inf padded).  Either may be NULL.
+__global__ void __launch_bounds__(256)
+col_heads_kernel(const ent_t *__restrict__ col_buf, const unsigned int *__restrict__ col_cnt,
+                 int64_t ny, int col_cap, int cap, int64_t row_offset, ent_t *__restrict__ out_ent,
+                 float *__restrict__ out_key) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ny * cap) return;
+    const int64_t col = idx / cap;
+    const int p = (int)(idx - col * cap);
+    const unsigned int total = col_cnt[col];
+    const int n = (int)min(min(total, (unsigned int)col_cap), (unsigned int)cap);
+    ent_t e = EMPTY_ENTRY;
+    if (p < n) e = col_buf[(size_t)col * col_cap + p] + (ent_t)row_offset;   // rows stay below 2^31
+    if (out_ent) out_ent[idx] = e;
+    if (out_key) out_key[idx] = entry_key(e);
+}
+
+// tau[col] = min(tau[col], kth smallest of the nparts x L keys gathered for the column): the
+// kth best key over the union of what every rank has seen bounds the column's final kth best
+// key from above.  One warp per column, bitonic sort over lanes x registers.
+template <int R>
+__global__ void __launch_bounds__(128)
+kth_key_kernel(const float *__restrict__ keys, int nparts, int64_t part_stride, int64_t ny, int L,
+               int kth, float *__restrict__ tau) {
+    const int lane = threadIdx.x & 31;
+    const int64_t col = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (col >= ny) return;
+    const int total = nparts * L;
+    ent_t x[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = r * 32 + lane;
+        float v = INFINITY;
+        if (i < total) {
+            const int part = i / L, j = i - part * L;
+            v = keys[(size_t)part * part_stride + (size_t)col * L + j];
+        }
+        x[r] = pack_entry(v, 0);
+    }
+    warp_sort_entries<R>(x, lane);
+    ent_t kth_ent = EMPTY_ENTRY;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const ent_t w = __shfl_sync(FULL_MASK, x[r], (kth - 1) & 31);
+        if (r == ((kth - 1) >> 5)) kth_ent = w;
+    }
+    if (lane == 0) tau[col] = fminf(tau[col], entry_key(kth_ent));
+}
+
 static size_t fused_stage_bytes(int bk) { return (size_t)(2 * BM + 2 * F_HALF) * bk * 4; }
 
 template <int BK>
@@ -455,4 +509,40 @@ extern "C" int kb2_col_compact(uint64_t *col_buf, uint32_t *col_cnt, int64_t ny,
     if (ny == 0) return 0;
     return col_select_launch(true, col_buf, col_cnt, ny, col_cap, cap, nullptr, nullptr, tau_col,
                              nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int kb2_col_heads(const uint64_t *col_buf, const uint32_t *col_cnt, int64_t ny,
+                             int col_cap, int cap, int64_t row_offset, uint64_t *out_entries,
+                             float *out_keys, void *stream) {
+    KB2_CHECK(ny >= 0 && cap > 0 && col_cap >= cap && col_cap <= 4096, "col_heads: bad arguments");
+    KB2_CHECK(col_buf && col_cnt && (out_entries || out_keys), "col_heads: NULL argument");
+    KB2_CHECK(row_offset >= 0 && row_offset < (1LL << 31), "col_heads: row_offset out of range");
+    if (ny == 0) return 0;
+    const int64_t total = ny * cap;
+    col_heads_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const ent_t *>(col_buf), col_cnt, ny, col_cap, cap, row_offset,
+        reinterpret_cast<ent_t *>(out_entries), out_keys);
+    KB2_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int kb2_kth_key(const float *keys, int nparts, int64_t part_stride, int64_t ny, int L,
+                           int kth, float *tau, void *stream) {
+    KB2_CHECK(keys && tau && nparts >= 1 && L >= 1 && ny >= 0, "kth_key: bad arguments");
+    const int total = nparts * L;
+    KB2_CHECK(total <= 1024, "kth_key: %d keys per column exceed 1024", total);
+    KB2_CHECK(kth >= 1 && kth <= total, "kth_key: kth=%d outside [1, %d]", kth, total);
+    if (ny == 0) return 0;
+    const unsigned grid = (unsigned)ceil_div64(ny, 4);
+    cudaStream_t st = (cudaStream_t)stream;
+#define KB2_KTH(R) kth_key_kernel<R><<<grid, 128, 0, st>>>(keys, nparts, part_stride, ny, L, kth, tau)
+    if (total <= 32) KB2_KTH(1);
+    else if (total <= 64) KB2_KTH(2);
+    else if (total <= 128) KB2_KTH(4);
+    else if (total <= 256) KB2_KTH(8);
+    else if (total <= 512) KB2_KTH(16);
+    else KB2_KTH(32);
+#undef KB2_KTH
+    KB2_LAUNCH_CHECK();
+    return 0;
 }

@@ -1,12 +1,19 @@
 """Multi-GPU exact kNN: one process per GPU (torch.distributed, NCCL over NVLink).
 
-The index side of each pass is sharded by rows over the ranks (forward pass: target
-rows; reverse pass: source rows -- SURVEY.md section 8e); queries are replicated.
+One-direction passes: the index side is sharded by rows over the ranks (forward pass:
+target rows; reverse pass: source rows -- SURVEY.md section 8e); queries are replicated.
 Every rank searches its shard for all queries (candidate search + exact finish,
 ids made global with the shard's base), the per-shard top-k lists are exchanged
 with ONE all-gather, and a GPU merge kernel (kb2_topk_rows, nparts = world size)
 keeps the k best per query.  The result is replicated on every rank, so the
 rescaling that follows needs no further communication.
+
+Dual-direction pass (kiez's reverse + forward kNN from one contraction, the default at
+BASELINE.json's metric config): the SOURCE rows are sharded (`sharded_knn_both_rows` +
+`RowShardComm`); every rank contracts its rows with all targets, the ranks agree on the
+per-target thresholds between row segments and each rank finishes a shard of the targets.
+`sharded_knn_both` (target shards, per-rank thresholds) remains for problems too small to
+give every rank a few row tiles.
 
 `shard_bounds`, the gather layout and the merge are backend-agnostic
 (`sharded_topk`), which is how the world_size-2 gloo tests exercise them on CPU.
@@ -145,70 +152,115 @@ def sharded_knn_both(algo, rows, cols, k_fwd: int, k_rev: int, exclude_self_rows
     return fwd, (rev_d, rev_i)
 
 
-def sharded_knn_both_grid(algo, rows, cols, k_fwd: int, k_rev: int, exclude_self_rows: bool,
-                          grid: Tuple[int, int], group=None, merge=None):
-    """Dual-direction pass on an R x C grid of ranks (R * C = world size): rank (r, c) =
-    divmod(rank, C) contracts row block r with column block c.  Compared with the column shards
-    of `sharded_knn_both` (= grid (1, world)) every row list sees world / R times more columns
-    (a shorter list fill phase per flop) and every rank finishes only n / R row lists; the price
-    is a second merge: row-wise lists are merged across the C column blocks of a row block,
-    column-wise lists across the R row blocks of a column block.  Two packed all-gathers, as
-    before.  EXPERIMENTAL: host logic covered by the gloo tests, not yet the default (DESIGN.md
-    round-2 list).  Returns ((fwd_dist, fwd_ind), (rev_dist, rev_ind)), identical on every rank."""
-    merge = device_merge if merge is None else merge
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    n_r, n_c = grid
-    if n_r * n_c != world:
-        raise ValueError(f"grid {grid} does not match world size {world}")
-    r, c = divmod(rank, n_c)
-    per_r, per_c = -(-rows.n // n_r), -(-cols.n // n_c)
-    r0, r1 = min(rows.n, r * per_r), min(rows.n, (r + 1) * per_r)
-    c0, c1 = min(cols.n, c * per_c), min(cols.n, (c + 1) * per_c)
-    dev = algo.device
-    inf = float("inf")
-    # padded per-rank results: slots a block cannot fill hold +inf / -1
-    fd = torch.full((per_r, k_fwd), inf, dtype=torch.float64, device=dev)
-    fi = torch.full((per_r, k_fwd), -1, dtype=torch.int64, device=dev)
-    rd = torch.full((per_c, k_rev), inf, dtype=torch.float64, device=dev)
-    ri = torch.full((per_c, k_rev), -1, dtype=torch.int64, device=dev)
-    if r1 > r0 and c1 > c0:
-        kf, kr = min(k_fwd, c1 - c0), min(k_rev, r1 - r0)
-        (bfd, bfi), (brd, bri) = algo.search_both(rows.rows(r0, r1), cols.rows(c0, c1), kf, kr,
-                                                  exclude_self_rows=exclude_self_rows)
-        fd[: r1 - r0, :kf], fi[: r1 - r0, :kf] = bfd, bfi
-        rd[: c1 - c0, :kr], ri[: c1 - c0, :kr] = brd, bri
+class RowShardComm:
+    """The collectives of the row-sharded dual-direction pass (`B200.search_both(comm=...)`).
 
-    def gather(d, i):
-        n_loc, k = d.shape
-        packed = torch.empty(2 * n_loc * k, dtype=torch.int64, device=dev)
+    Every rank runs the pass over ITS rows against all columns.  Row-wise results are then
+    complete per rank; the per-column state has to agree across ranks:
+      * thresholds: after the sample search and between row segments every rank contributes its
+        best keys per column, `kth_over_ranks` all-gathers them and keeps the kth best of the
+        union -- the ranks continue with ONE threshold per column, so a column receives as
+        many emits in total as in a single-GPU run (with per-rank thresholds it would receive
+        that many PER RANK, which is what capped the column-shard scheme at 0.66 efficiency
+        on 8 GPUs);
+      * result: after the last segment `columns_to_owners` sends, with one all-to-all, the head
+        of every column (each rank's best `cap` rows) to the rank that owns the column; the
+        owner merges the `world` heads and runs the exact finish for its columns only.
+    `kth` is injectable so that the world_size-2 gloo tests can run the layer on CPU tensors."""
+
+    def __init__(self, rows_full, group=None, kth=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.rows_full = rows_full          # every rank holds all rows (needed by the owners' finish)
+        self.n_rows = rows_full.n
+        self._kth = kth if kth is not None else self._device_kth
+
+    @staticmethod
+    def _device_kth(gathered, nparts, m, width, kth, tau):
+        from . import _lib as lib
+
+        with torch.cuda.device(tau.device):
+            lib.call("kb2_kth_key", lib.ptr(gathered), nparts, m * width, m, width, kth, lib.ptr(tau),
+                     lib.stream_ptr())
+
+    def kth_over_ranks(self, keys, kth, tau=None):
+        """keys [m][width] fp32 (this rank's best keys per column, +inf padded) -> tau [m] =
+        min(tau, kth smallest over the ranks' keys).  One all-gather of m * width * 4 bytes."""
+        m, width = keys.shape
+        gathered = torch.empty((self.world, m, width), dtype=torch.float32, device=keys.device)
+        dist.all_gather_into_tensor(gathered.view(-1), keys.contiguous().view(-1), group=self.group)
+        if tau is None:
+            tau = torch.full((m,), float("inf"), dtype=torch.float32, device=keys.device)
+        self._kth(gathered, self.world, m, width, kth, tau)
+        return tau
+
+    def max_(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return t
+
+    def min_(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        return t
+
+    def max_scalar(self, x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device=self.rows_full.raw.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return float(t.item())
+
+    def column_shard(self, m: int) -> Tuple[int, int, int]:
+        """(c0, c1, per): rank r owns the columns [r * per, min(m, (r + 1) * per))."""
+        per = -(-m // self.world)
+        return min(m, self.rank * per), min(m, (self.rank + 1) * per), per
+
+    def columns_to_owners(self, heads, pad_value):
+        """heads [m][cap] int64 (this rank's best rows per column) -> (recv [world][per][cap]:
+        the heads of this rank's column shard from every rank, c0, c1).  One all-to-all."""
+        m, cap = heads.shape
+        c0, c1, per = self.column_shard(m)
+        send = heads
+        if self.world * per != m:
+            send = torch.full((self.world * per, cap), pad_value, dtype=heads.dtype, device=heads.device)
+            send[:m] = heads
+        recv = torch.empty((self.world, per, cap), dtype=heads.dtype, device=heads.device)
+        dist.all_to_all_single(recv.view(-1), send.contiguous().view(-1), group=self.group)
+        return recv, c0, c1
+
+    def gather_blocks(self, d, i, total: int, per: int, bounds):
+        """Per-rank result blocks (rows bounds(r) of the full result, at most `per` each) ->
+        the full (total, k) result on every rank: one packed all-gather (dist bits | ind)."""
+        k = d.shape[1]
+        n_loc = d.shape[0]
+        packed = torch.zeros(2 * per * k, dtype=torch.int64, device=d.device)
         packed[: n_loc * k] = d.contiguous().view(torch.int64).reshape(-1)
-        packed[n_loc * k:] = i.reshape(-1)
-        gathered = torch.empty(world * packed.numel(), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(gathered, packed, group=group)
-        return gathered, packed.numel()
+        packed[per * k: per * k + n_loc * k] = i.reshape(-1)
+        gathered = torch.empty(self.world * 2 * per * k, dtype=torch.int64, device=d.device)
+        dist.all_gather_into_tensor(gathered, packed, group=self.group)
+        g = gathered.view(self.world, 2, per, k)
+        out_d = torch.empty((total, k), dtype=torch.float64, device=d.device)
+        out_i = torch.empty((total, k), dtype=torch.int64, device=d.device)
+        for r in range(self.world):
+            lo, hi = bounds(r)
+            out_d[lo:hi] = g[r, 0, : hi - lo].view(torch.float64)
+            out_i[lo:hi] = g[r, 1, : hi - lo]
+        return out_d, out_i
 
-    # row-wise: for row block b, the parts are the C consecutive ranks b * C .. b * C + C - 1
-    g, size = gather(fd, fi)
-    fwd_d = torch.empty((rows.n, k_fwd), dtype=torch.float64, device=dev)
-    fwd_i = torch.empty((rows.n, k_fwd), dtype=torch.int64, device=dev)
-    for b in range(n_r):
-        lo, hi = min(rows.n, b * per_r), min(rows.n, (b + 1) * per_r)
-        if hi <= lo:
-            continue
-        base = b * n_c * size
-        md, mi = merge(g[base:].view(torch.float64), g[base + per_r * k_fwd:], n_c, size, k_fwd, per_r)
-        fwd_d[lo:hi], fwd_i[lo:hi] = md[: hi - lo], mi[: hi - lo]
-    # column-wise: for column block b, the parts are ranks b, b + C, ..., b + (R - 1) * C
-    g, size = gather(rd, ri)
-    rev_d = torch.empty((cols.n, k_rev), dtype=torch.float64, device=dev)
-    rev_i = torch.empty((cols.n, k_rev), dtype=torch.int64, device=dev)
-    for b in range(n_c):
-        lo, hi = min(cols.n, b * per_c), min(cols.n, (b + 1) * per_c)
-        if hi <= lo:
-            continue
-        base = b * size
-        md, mi = merge(g[base:].view(torch.float64), g[base + per_c * k_rev:], n_r, n_c * size, k_rev,
-                       per_c)
-        rev_d[lo:hi], rev_i[lo:hi] = md[: hi - lo], mi[: hi - lo]
-    return (fwd_d, fwd_i), (rev_d, rev_i)
+
+def sharded_knn_both_rows(algo, rows, cols, k_fwd: int, k_rev: int, exclude_self_rows: bool,
+                          group=None, comm=None):
+    """Distributed dual-direction pass with the ROWS (sources) sharded: rank r runs
+    `search_both` over its contiguous row shard against all columns with `RowShardComm`
+    agreeing the column state across ranks; the forward result of its rows and the reverse result
+    of its column shard are then replicated with one packed all-gather each.
+    Returns ((fwd_dist, fwd_ind), (rev_dist, rev_ind)), identical on every rank."""
+    comm = RowShardComm(rows, group) if comm is None else comm
+    world, rank = comm.world, comm.rank
+    lo, hi = shard_bounds(rows.n, world, rank)
+    (fd, fi), (rd, ri) = algo.search_both(rows.rows(lo, hi), cols, k_fwd, k_rev,
+                                          exclude_self_rows=exclude_self_rows, comm=comm)
+    per_rows = -(-rows.n // world)
+    fwd = comm.gather_blocks(fd, fi, rows.n, per_rows, lambda r: shard_bounds(rows.n, world, r))
+    per_cols = -(-cols.n // world)
+    rev = comm.gather_blocks(rd, ri, cols.n, per_cols,
+                             lambda r: (min(cols.n, r * per_cols), min(cols.n, (r + 1) * per_cols)))
+    return fwd, rev

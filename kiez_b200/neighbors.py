@@ -256,7 +256,7 @@ class B200Mixin:
     def __init__(self, n_candidates: int = 5, metric: str = "euclidean", p: int = 2,
                  device: Optional[Any] = None, impl: str = "auto", center: bool = True,
                  distributed: Optional[bool] = None, fused: Any = "auto",
-                 precision: str = "auto", n_jobs=None, shard_grid: Optional[Tuple[int, int]] = None):
+                 precision: str = "auto", n_jobs=None, shard_mode: Optional[str] = None):
         if torch is None or not torch.cuda.is_available():
             raise ImportError(
                 "The B200 backend needs PyTorch with a CUDA device (sm_100a); there is no "
@@ -293,13 +293,13 @@ class B200Mixin:
         # numpy callers in distributed runs: "all" = every rank copies the (replicated) result
         # to its host, "rank0" = only rank 0 does (the others keep device tensors)
         self.host_result = "all"
-        # EXPERIMENTAL (off by default): run the dual-direction pass on an R x C grid of ranks
-        # instead of column shards (distributed.sharded_knn_both_grid); KB2_SHARD_GRID="RxC"
-        if shard_grid is None and os.environ.get("KB2_SHARD_GRID"):
-            shard_grid = tuple(int(v) for v in os.environ["KB2_SHARD_GRID"].lower().split("x"))
-        if shard_grid is not None and (len(shard_grid) != 2 or min(shard_grid) < 1):
-            raise ValueError(f"shard_grid must be (R, C) with R, C >= 1, got {shard_grid!r}")
-        self.shard_grid = tuple(shard_grid) if shard_grid is not None else None
+        # distributed dual-direction pass: "rows" = every rank takes a shard of the source rows and
+        # the ranks agree on the column thresholds (default), "cols" = column (target) shards
+        if shard_mode is None:
+            shard_mode = os.environ.get("KB2_SHARD_MODE", "rows")
+        if shard_mode not in ("rows", "cols"):
+            raise ValueError(f"shard_mode must be 'rows' or 'cols', got {shard_mode!r}")
+        self.shard_mode = shard_mode
         if fused not in ("auto", True, False):
             raise ValueError(f"fused must be 'auto', True or False, got {fused!r}")
         self.fused = fused
@@ -391,15 +391,15 @@ class B200Mixin:
             # forward pass that HubnessReduction.kneighbors will ask for next (base.py:92-94)
             single = bool(getattr(self, "source_equals_target", False))
             k_fwd = min(self.n_candidates, target_index.n - (1 if single else 0))
-            if self.distributed and self.shard_grid is not None:
-                from .distributed import sharded_knn_both_grid
+            if self.distributed:
+                from .distributed import sharded_knn_both, sharded_knn_both_rows
 
-                fwd, rev = sharded_knn_both_grid(self, source_index, target_index, k_fwd, k, single,
-                                                 self.shard_grid)
-            elif self.distributed:
-                from .distributed import sharded_knn_both
-
-                fwd, rev = sharded_knn_both(self, source_index, target_index, k_fwd, k, single)
+                world = torch.distributed.get_world_size()
+                cap = candidate_capacity(max(k, self.n_candidates))
+                # rows sharded (default): needs a few full tiles of rows per rank; else columns
+                by_rows = self.shard_mode == "rows" and source_index.n // world >= max(1024, 8 * cap)
+                shard = sharded_knn_both_rows if by_rows else sharded_knn_both
+                fwd, rev = shard(self, source_index, target_index, k_fwd, k, single)
             else:
                 fwd, rev = self.search_both(source_index, target_index, k_fwd, k,
                                             exclude_self_rows=single)
@@ -570,7 +570,8 @@ class B200Mixin:
                 cap = boosted
         return cap
 
-    def _screen_verdict(self, unverified, cap: int = 0, dpad: int = 0, dual: bool = False) -> bool:
+    def _screen_verdict(self, unverified, cap: int = 0, dpad: int = 0, dual: bool = False,
+                        comm=None) -> bool:
         """Record (once per fit and list length) whether the screen carries on as configured,
         from the `unverified` flags of the probe rows; one host sync.  False = start over
         (`_screen_boost` or `_screen_ok` changed)."""
@@ -578,6 +579,8 @@ class B200Mixin:
             return True
         if self._screen_ok is None:
             frac = float(unverified.to(torch.float32).mean()) if unverified.numel() else 0.0
+            if comm is not None:
+                frac = comm.max_scalar(frac)       # every rank must take the same branch
             self.search_stats.setdefault("screen_probe_unverified", []).append(frac)
             can_boost = (not self._screen_boost and cap > 0 and self._boosted_capacity(cap) > cap
                          and self._lib.lib.kb2_screen_stages(dpad, self._boosted_capacity(cap),
@@ -695,10 +698,11 @@ class B200Mixin:
             return False
         if self.fused is True:
             return True
-        # auto: only where the pass is tensor-bound (measured: with d = 128 or long candidate
-        # lists the doubled epilogue is the limiter and two passes are faster), and only for
-        # problems large enough to amortise the threshold sample
-        if cap > 32 or rows.dpad < 192 or rows.n * cols.n < (1 << 32):
+        # auto: only where the pass is tensor-bound (measured: with d = 128 the doubled epilogue
+        # is the limiter and two passes are faster; at d = 256 the pass wins for every list
+        # length it takes: C4 at c = 50 runs 1388 ms against 2165 ms for two screen passes),
+        # and only for problems large enough to amortise the threshold sample
+        if rows.dpad < 192 or rows.n * cols.n < (1 << 32):
             return False
         # the column buffers must fit; decided from rank-independent quantities only (shapes,
         # world size, the device's TOTAL memory) so that every rank of a distributed run takes
@@ -729,12 +733,21 @@ class B200Mixin:
         return bounds
 
     def search_both(self, rows: PreparedRows, cols: PreparedRows, k_rows: int, k_cols: int,
-                    exclude_self_rows: bool = False):
+                    exclude_self_rows: bool = False, comm=None):
         """One contraction, both directions: ((dist, ind) of every row's k_rows nearest columns,
-        (dist, ind) of every column's k_cols nearest rows)."""
+        (dist, ind) of every column's k_cols nearest rows).
+
+        `comm` (distributed.RowShardComm): this rank holds a SHARD of the rows.  The row side
+        is then complete per rank (every column is visited locally); the column side is agreed
+        across ranks -- the thresholds through an all-gather of each column's best keys after
+        the sample and between row segments, the result through an all-to-all of the column
+        heads after the last one -- and each rank finishes a shard of the columns.  Returns
+        (forward result of the own rows, reverse result of the own column shard)."""
         lib = self._lib
         dev = self.device
         cap = self._capacity(max(k_rows, k_cols), rows, dual=True)
+        world = comm.world if comm is not None else 1
+        n_total = comm.n_rows if comm is not None else rows.n
         with torch.cuda.device(dev):
             st = lib.stream_ptr()
             sm = torch.cuda.get_device_properties(dev).multi_processor_count
@@ -742,8 +755,10 @@ class B200Mixin:
             prof = getattr(self, "_profile", None)       # bench.py: CUDA events around the searches
             cols.ensure()
             # 1. column thresholds from a strided sample of the rows (a host matrix still being
-            #    uploaded sent exactly these rows ahead, see _start_uploads)
-            n_s = self._fused_sample_rows(rows.n, cap)
+            #    uploaded sent exactly these rows ahead, see _start_uploads); with sharded rows
+            #    every rank searches its share of the sample
+            n_s_total = self._fused_sample_rows(n_total, cap)
+            n_s = n_s_total if comm is None else max(1, min(n_total // world, -(-n_s_total // world)))
             step = max(1, rows.n // n_s)
             if rows.presample is not None and rows.presample[0] == (n_s, step):
                 sample = rows.presample[1].ensure()
@@ -766,7 +781,10 @@ class B200Mixin:
                     ev1.record()
                     prof.append((ev0, ev1, cols.n, n_s, rows.d, "tf32x3"))
             # the cap-th best within ANY subset of the rows bounds the final cap-th best
-            tau = s_key.view(cols.n, lists, cap)[:, :, cap - 1].amin(dim=1).contiguous()
+            if comm is None:
+                tau = s_key.view(cols.n, lists, cap)[:, :, cap - 1].amin(dim=1).contiguous()
+            else:
+                tau = comm.kth_over_ranks(s_key, cap)      # cap-th best over the ranks' samples
             del _s_idx, s_key, sample
             # 2. the dual-direction pass, one launch per row segment; exact finish of the row
             #    lists per segment; thresholds tighten between segments
@@ -775,27 +793,29 @@ class B200Mixin:
             col_buf = torch.empty((cols.n, col_cap), dtype=torch.int64, device=dev)
             fwd_d = torch.empty((rows.n, k_rows), dtype=torch.float64, device=dev)
             fwd_i = torch.empty((rows.n, k_rows), dtype=torch.int64, device=dev)
-            unv_rows = torch.empty((rows.n,), dtype=torch.int32, device=dev) if screen else None
-            bounds = self._fused_segments(rows.n, n_s)
+            unv_rows = torch.zeros((rows.n,), dtype=torch.int32, device=dev) if screen else None
+            bounds = self._fused_segments(n_total, n_s_total)
+            if comm is not None:
+                # the same number of segments on every rank (the exchanges between them are
+                # collective), each a proportional share of the global segment
+                bounds = [min(rows.n, (int(b * rows.n / n_total) + 255) // 256 * 256) for b in bounds]
+                bounds[0], bounds[-1] = 0, rows.n
+                bounds = [max(b, p) for b, p in zip(bounds, [0] + bounds[:-1])]
             # statistics for bench.py / tests (extra reductions and host syncs): only on request
             stats = bool(getattr(self, "_collect_stats", False))
             emitted = torch.zeros((), dtype=torch.int64, device=dev) if stats else None
-            for lo, hi in zip(bounds[:-1], bounds[1:]):
-                seg = rows.rows(lo, hi)
-                if screen:
+            for s_no, (lo, hi) in enumerate(zip(bounds[:-1], bounds[1:])):
+                last = s_no == len(bounds) - 2
+                seg = rows.rows(lo, hi) if hi > lo else None
+                if seg is None:
+                    pass                                    # a rank without rows in this segment
+                elif screen:
                     cand_rows, key_rows, r_lists = self._screen_search(
                         seg, cols, cap, dual=(tau, col_cnt, col_buf, col_cap, lo))
                     self._refine_checked(seg, cols, cand_rows, k_rows, exclude_self_rows,
                                          lib.ptr(key_rows) + 4 * (cap - 1), r_lists * cap, cap, r_lists,
                                          out=(fwd_d[lo:hi], fwd_i[lo:hi], unv_rows[lo:hi]))
-                    del key_rows
-                    if lo == 0 and len(bounds) > 2 and not self._screen_verdict(
-                            unv_rows[lo:hi], cap, rows.dpad, dual=True):
-                        # probe failed: start over with longer lists, or with 3xTF32 keys
-                        # (_capacity / _use_screen now answer differently)
-                        del cand_rows, col_buf, col_cnt, fwd_d, fwd_i, unv_rows, tau
-                        return self.search_both(rows, cols, k_rows, k_cols,
-                                                exclude_self_rows=exclude_self_rows)
+                    del key_rows, cand_rows
                 else:
                     splits = lib.lib.kb2_suggest_splits(seg.n, cols.n, cap, sm)
                     cand_rows = torch.empty((seg.n, splits * cap), dtype=torch.int32, device=dev)
@@ -812,47 +832,93 @@ class B200Mixin:
                         prof.append((ev0, ev1, seg.n, cols.n, rows.d, "tf32x3-dual"))
                     self._refine(seg, cols, cand_rows, k_rows, exclude_self_rows,
                                  out=(fwd_d[lo:hi], fwd_i[lo:hi]))
-                del cand_rows
-                if hi < rows.n:
+                    del cand_rows
+                if screen and s_no == 0 and len(bounds) > 2 and not self._screen_verdict(
+                        unv_rows[lo:hi], cap, rows.dpad, dual=True, comm=comm):
+                    # probe failed: start over with longer lists, or with 3xTF32 keys
+                    # (_capacity / _use_screen now answer differently)
+                    del col_buf, col_cnt, fwd_d, fwd_i, unv_rows, tau
+                    return self.search_both(rows, cols, k_rows, k_cols,
+                                            exclude_self_rows=exclude_self_rows, comm=comm)
+                if not last or comm is not None:
+                    # best cap rows to the head of every column buffer, tau = cap-th best so far
                     if emitted is not None:     # sticky overflow counts are not emits
                         emitted += torch.where(col_cnt < (1 << 30), col_cnt, 0).sum()
                     lib.call("kb2_col_compact", lib.ptr(col_buf), lib.ptr(col_cnt), cols.n, col_cap,
                              cap, lib.ptr(tau), st)
                     if emitted is not None:
                         emitted -= torch.where(col_cnt < (1 << 30), col_cnt, 0).sum()
+                    if comm is not None and not last:
+                        # ... over the rows of ALL ranks: exchange the heads' keys
+                        keys = torch.empty((cols.n, cap), dtype=torch.float32, device=dev)
+                        lib.call("kb2_col_heads", lib.ptr(col_buf), lib.ptr(col_cnt), cols.n, col_cap,
+                                 cap, 0, None, lib.ptr(keys), st)
+                        comm.kth_over_ranks(keys, cap, tau=tau)
+                        del keys
             rows.ensure()
+            bad_rows = torch.zeros(0, dtype=torch.int64, device=dev)
             if screen:
                 self.search_stats["screen_rows"] += rows.n
                 bad_rows = torch.nonzero(unv_rows).flatten()
                 self._research(rows, cols, bad_rows, k_rows, exclude_self_rows, fwd_d, fwd_i)
             fwd = (fwd_d, fwd_i)
             # 3. column side: best cap emitted rows per column, exact finish
-            cand_cols = torch.empty((cols.n, cap), dtype=torch.int32, device=dev)
-            overflow = torch.empty(cols.n, dtype=torch.int32, device=dev)
-            col_tau = torch.empty(cols.n, dtype=torch.float32, device=dev) if screen else None
-            lib.call("kb2_col_select", lib.ptr(col_buf), lib.ptr(col_cnt), cols.n, col_cap, cap,
-                     lib.ptr(cand_cols), lib.ptr(overflow), lib.ptr(tau) if screen else None,
-                     lib.ptr(col_tau), st)
+            if comm is None:
+                q_cols, y_rows, c0 = cols, rows, 0
+                cand_cols = torch.empty((cols.n, cap), dtype=torch.int32, device=dev)
+                overflow = torch.empty(cols.n, dtype=torch.int32, device=dev)
+                col_tau = torch.empty(cols.n, dtype=torch.float32, device=dev) if screen else None
+                lib.call("kb2_col_select", lib.ptr(col_buf), lib.ptr(col_cnt), cols.n, col_cap, cap,
+                         lib.ptr(cand_cols), lib.ptr(overflow), lib.ptr(tau) if screen else None,
+                         lib.ptr(col_tau), st)
+            else:
+                # every rank holds the best cap of ITS rows per column (heads after the final
+                # compaction) and a bound tau for everything it did not keep; the owner of a
+                # column shard merges the W heads and finishes against ALL rows
+                heads = torch.empty((cols.n, cap), dtype=torch.int64, device=dev)
+                lib.call("kb2_col_heads", lib.ptr(col_buf), lib.ptr(col_cnt), cols.n, col_cap, cap,
+                         rows.base, lib.ptr(heads), None, st)
+                lost = ((col_cnt >= (1 << 30)) | (col_cnt > col_cap)).to(torch.int32)
+                comm.max_(lost)
+                comm.min_(tau)
+                recv, c0, c1 = comm.columns_to_owners(heads, lib.EMPTY_ENTRY)
+                del heads
+                m_loc = c1 - c0
+                q_cols, y_rows = cols.rows(c0, c1), comm.rows_full
+                buf2 = recv.permute(1, 0, 2)[:m_loc].reshape(m_loc, world * cap).contiguous()
+                cnt2 = torch.full((m_loc,), world * cap, dtype=torch.int32, device=dev)
+                cand_cols = torch.empty((m_loc, cap), dtype=torch.int32, device=dev)
+                overflow = torch.empty(m_loc, dtype=torch.int32, device=dev)
+                tau_loc = tau[c0:c1].contiguous()
+                col_tau = torch.empty(m_loc, dtype=torch.float32, device=dev)
+                if m_loc:
+                    lib.call("kb2_col_select", lib.ptr(buf2), lib.ptr(cnt2), m_loc, world * cap, cap,
+                             lib.ptr(cand_cols), lib.ptr(overflow), lib.ptr(tau_loc), lib.ptr(col_tau), st)
+                # what the merge dropped is bounded by its cap-th key, what a rank never kept by
+                # that rank's bound
+                col_tau = torch.minimum(col_tau, tau_loc)
+                overflow = lost[c0:c1].contiguous()
+                del recv, buf2
             del col_buf
             if screen:
-                rev_d, rev_i, unv = self._refine_checked(cols, rows, cand_cols, k_cols, False,
+                rev_d, rev_i, unv = self._refine_checked(q_cols, y_rows, cand_cols, k_cols, False,
                                                          lib.ptr(col_tau), 1, 1, 1)
-                self.search_stats["screen_rows"] += cols.n
+                self.search_stats["screen_rows"] += q_cols.n
                 n_over = int(overflow.sum()) if stats else 0
                 # overflowed columns lost rows below their threshold: search them again too
                 bad_cols = torch.nonzero(unv | overflow).flatten()
-                self._research(cols, rows, bad_cols, k_cols, False, rev_d, rev_i)
-                # local ids of the rows / columns that took the 3xTF32 re-search (parity samples
+                self._research(q_cols, y_rows, bad_cols, k_cols, False, rev_d, rev_i)
+                # global ids of the rows / columns that took the 3xTF32 re-search (parity samples
                 # of the tests and bench.py force-include them)
-                self.researched = {"rows": bad_rows + rows.base, "cols": bad_cols + cols.base}
+                self.researched = {"rows": bad_rows + rows.base, "cols": bad_cols + q_cols.base}
             else:
-                rev_d, rev_i = self._refine(cols, rows, cand_cols, k_cols, False)
+                rev_d, rev_i = self._refine(q_cols, y_rows, cand_cols, k_cols, False)
                 # overflowed columns lost rows; a column whose threshold TIES with its cap-th
                 # best key (duplicate rows: emits are strictly below tau) may hold fewer than k
                 bad = torch.nonzero(overflow.bool() | (rev_i[:, k_cols - 1] < 0)).flatten()
                 n_over = int(bad.numel())
                 if bad.numel():      # columns whose buffer overflowed: plain search for those few
-                    d_b, i_b = self._search_tf32x3(cols.take(bad), rows, k_cols)
+                    d_b, i_b = self._search_tf32x3(q_cols.take(bad), y_rows, k_cols)
                     rev_d[bad] = d_b
                     rev_i[bad] = i_b
             if stats:
@@ -860,6 +926,7 @@ class B200Mixin:
                 self._fused_stats = {"sample_rows": int(n_s), "col_cap": int(col_cap),
                                      "row_segments": [int(b) for b in bounds],
                                      "emitted_per_column_mean": float(emitted) / max(1, cols.n),
+                                     "emitted_scope": "this rank's rows" if comm is not None else "all rows",
                                      "overflow_columns": n_over}
         return fwd, (rev_d, rev_i)
 

@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from kiez_b200.distributed import (shard_bounds, sharded_knn_both, sharded_knn_both_grid,
+from kiez_b200.distributed import (RowShardComm, shard_bounds, sharded_knn_both, sharded_knn_both_rows,
                                    sharded_topk, upload_sharded)
 from oracle import kiez_oracle as O
 
@@ -188,38 +188,105 @@ def test_sharded_knn_both_world2_gloo(nx, ny, k, single):
                                  1e-12, what=f"rev rank{rank}")
 
 
-def _grid_worker(rank, world, port, x, y, k, single, grid, out):
+EMPTY = np.int64(0xFF800000FFFFFFFF - (1 << 64))
+
+
+def _pack(key, row):
+    """select.cuh pack_entry on the host: order-preserving fp32 key bits << 32 | row."""
+    u = np.asarray(key, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = np.where((u >> np.uint64(31)) == 1, u ^ np.uint64(0xFFFFFFFF), u ^ np.uint64(0x80000000))
+    return ((u << np.uint64(32)) | np.asarray(row, dtype=np.uint64)).view(np.int64)
+
+
+def _numpy_kth(gathered, nparts, m, width, kth, tau):
+    """kb2_kth_key on CPU tensors: tau = min(tau, kth smallest of the gathered keys)."""
+    g = gathered.numpy().transpose(1, 0, 2).reshape(m, nparts * width)
+    tau.copy_(torch.minimum(tau, torch.from_numpy(np.sort(g, axis=1)[:, kth - 1].copy())))
+
+
+class _RowShardOracleAlgo:
+    """`B200.search_both(comm=...)` restated with numpy on the host: the same protocol -- sample
+    thresholds agreed with `kth_over_ranks`, emits below the threshold, heads to the column
+    owners, merge, exact finish -- over float32 keys, so that the gloo test drives every
+    collective of `RowShardComm` exactly as the CUDA path does."""
+
+    device = torch.device("cpu")
+
+    def search_both(self, rows, cols, k_rows, k_cols, exclude_self_rows=False, comm=None):
+        cap = max(k_rows, k_cols) + 2
+        d2 = O._pairwise(rows.x, cols.x, "sqeuclidean")                 # [rows][cols]
+        key = d2.astype(np.float32)
+        # row side: complete per rank
+        d = np.sqrt(d2)
+        if exclude_self_rows:
+            r = np.arange(rows.n)
+            c = r + rows.base - cols.base
+            ok = (c >= 0) & (c < cols.n)
+            d[r[ok], c[ok]] = np.inf
+        order = np.argsort(d, axis=1, kind="stable")[:, :k_rows]
+        fwd = (torch.from_numpy(np.take_along_axis(d, order, 1)), torch.from_numpy(order + cols.base))
+        # thresholds: every rank's best keys against its share of the sample, kth over the ranks
+        n_s = max(1, rows.n // 3)
+        s_keys = np.full((cols.n, cap), np.inf, dtype=np.float32)
+        srt = np.sort(key[:n_s].T, axis=1)[:, :cap]
+        s_keys[:, : srt.shape[1]] = srt
+        tau = comm.kth_over_ranks(torch.from_numpy(s_keys), cap)
+        # emits strictly below the threshold; the best cap of them are the column's head
+        heads = np.full((cols.n, cap), EMPTY, dtype=np.int64)
+        bound = tau.numpy().copy()
+        for c in range(cols.n):
+            hit = np.flatnonzero(key[:, c] < bound[c])
+            best = hit[np.argsort(key[hit, c], kind="stable")][:cap]
+            heads[c, : len(best)] = _pack(key[best, c], best + rows.base)
+            if len(hit) >= cap:
+                bound[c] = key[best[-1], c]
+        tau = comm.min_(torch.from_numpy(bound))
+        recv, c0, c1 = comm.columns_to_owners(torch.from_numpy(heads), int(EMPTY))
+        merged = recv.numpy().transpose(1, 0, 2)[: c1 - c0].reshape(c1 - c0, -1)
+        merged = np.sort(merged.view(np.uint64), axis=1)[:, :cap]       # packed order = key order
+        ids = (merged & np.uint64(0xFFFFFFFF)).astype(np.int64)
+        ids[ids == 0xFFFFFFFF] = -1
+        # exact finish of the owner's columns against ALL rows
+        full = comm.rows_full.x
+        rd = np.full((c1 - c0, k_cols), np.inf)
+        ri = np.full((c1 - c0, k_cols), -1, dtype=np.int64)
+        for j in range(c1 - c0):
+            cand = ids[j][ids[j] >= 0]
+            dist_j = np.sqrt(((full[cand] - cols.x[c0 + j]) ** 2).sum(axis=1))
+            o = np.lexsort((cand, dist_j))[:k_cols]
+            rd[j, : len(o)], ri[j, : len(o)] = dist_j[o], cand[o]
+        return fwd, (torch.from_numpy(rd), torch.from_numpy(ri))
+
+
+def _rows_worker(rank, world, port, x, y, k, single, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        fwd, rev = sharded_knn_both_grid(_OracleAlgo(), _Rows(x), _Rows(y), k, k, single, grid,
-                                         merge=_numpy_merge)
+        rows = _Rows(x)
+        comm = RowShardComm(rows, kth=_numpy_kth)
+        fwd, rev = sharded_knn_both_rows(_RowShardOracleAlgo(), rows, _Rows(y), k, k, single,
+                                         comm=comm)
         out[rank] = tuple(t.numpy() for t in (*fwd, *rev))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize(("nx", "ny", "k", "single", "grid"), [
-    (41, 30, 4, False, (2, 2)), (37, 37, 5, True, (2, 2)), (40, 31, 4, False, (2, 1)),
-    (40, 31, 4, False, (1, 2)), (7, 5, 3, False, (2, 2))])
-def test_sharded_knn_both_grid_gloo(nx, ny, k, single, grid):
-    """R x C grid of ranks: row-wise lists merged across the column blocks of a row block,
-    column-wise lists across the row blocks of a column block; ragged blocks, self-exclusion
-    through the global bases, blocks smaller than k."""
-    rng = np.random.default_rng(nx * ny + grid[0])
-    x = rng.standard_normal((nx, 6))
-    y = x.copy() if single else rng.standard_normal((ny, 6))
-    world = grid[0] * grid[1]
+@pytest.mark.parametrize(("nx", "ny", "k", "single", "world"), [
+    (40, 31, 4, False, 2), (33, 33, 5, True, 2), (50, 37, 3, False, 3), (64, 10, 4, False, 2)])
+def test_sharded_knn_both_rows_gloo(nx, ny, k, single, world):
+    """Row-sharded dual-direction pass: thresholds agreed over the ranks (all-gather + kth),
+    column heads sent to the column owners (all-to-all, ragged column shards padded), both
+    results replicated with one all-gather each."""
+    rng = np.random.default_rng(nx * ny + world)
+    x = rng.standard_normal((nx, 6)).astype(np.float32).astype(np.float64)
+    y = x.copy() if single else rng.standard_normal((ny, 6)).astype(np.float32).astype(np.float64)
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_grid_worker, args=(world, _free_port(), x, y, k, single, grid, out), nprocs=world,
-             join=True)
-    k_fwd = min(k, ny - (1 if single else 0))
-    want_fd, want_fi = O.knn_brute(x, y, k_fwd, exclude_self=single)
-    want_rd, want_ri = O.knn_brute(y, x, min(k, nx))
+    mp.spawn(_rows_worker, args=(world, _free_port(), x, y, k, single, out), nprocs=world, join=True)
+    want_fd, want_fi = O.knn_brute(x, y, k, exclude_self=single)
+    want_rd, want_ri = O.knn_brute(y, x, k)
     for rank in range(world):
         fd, fi, rd, ri = out[rank]
-        O.assert_neighbors_match(fd[:, :k_fwd], fi[:, :k_fwd], want_fd, want_fi, 1e-12, 1e-12,
-                                 what=f"grid fwd rank{rank}")
-        O.assert_neighbors_match(rd[:, :min(k, nx)], ri[:, :min(k, nx)], want_rd, want_ri, 1e-12,
-                                 1e-12, what=f"grid rev rank{rank}")
+        assert fd.shape == (nx, k) and rd.shape == (y.shape[0], k)
+        O.assert_neighbors_match(fd, fi, want_fd, want_fi, 1e-9, 1e-9, what=f"rows fwd rank{rank}")
+        O.assert_neighbors_match(rd, ri, want_rd, want_ri, 1e-9, 1e-9, what=f"rows rev rank{rank}")

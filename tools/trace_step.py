@@ -24,6 +24,10 @@ def main():
     ap.add_argument("--c", type=int, default=10)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--min-gap-us", type=float, default=200.0)
+    ap.add_argument("--hubness", default="CSLS")
+    ap.add_argument("--method", default=None, help="hubness method kwarg (nicdm, normal, ...)")
+    ap.add_argument("--fused", default="auto", choices=["auto", "on", "off"])
+    ap.add_argument("--shard-mode", default="rows", choices=["rows", "cols"])
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -40,8 +44,12 @@ def main():
     tgt = torch.randn((args.m, args.d), generator=g, device=dev)
 
     def step():
-        inst = Kiez(n_candidates=args.c, algorithm=B200(n_candidates=args.c, distributed=world > 1),
-                    hubness="CSLS")
+        inst = Kiez(n_candidates=args.c,
+                    algorithm=B200(n_candidates=args.c, distributed=world > 1,
+                                   shard_mode=args.shard_mode,
+                                   fused={"auto": "auto", "on": True, "off": False}[args.fused]),
+                    hubness=None if args.hubness.lower() == "none" else args.hubness,
+                    hubness_kwargs={"method": args.method} if args.method else {})
         inst.fit(src, tgt)
         return inst.kneighbors(args.k)
 
@@ -72,6 +80,14 @@ def main():
     print("largest device activities:")
     for e in sorted(evs, key=lambda e: e.time_range.start - e.time_range.end)[:12]:
         print(f"  {1e-3 * (e.time_range.end - e.time_range.start):8.2f} ms  {e.name[:90]}")
+    print("device time by activity name:")
+    by_name = {}
+    for e in evs:
+        t = by_name.setdefault(e.name[:70], [0.0, 0])
+        t[0] += e.time_range.end - e.time_range.start
+        t[1] += 1
+    for name, (us, cnt) in sorted(by_name.items(), key=lambda kv: -kv[1][0])[:25]:
+        print(f"  {1e-3 * us:9.2f} ms  x{cnt:<4d} {name}")
     if world > 1:
         dist.destroy_process_group()
 
