@@ -37,6 +37,7 @@ WORKLOADS = {
     "c3": dict(n=100_000, m=100_000, d=256, c=100, k=10, hubness="MutualProximity"),
     "c4": dict(n=1_000_000, m=1_000_000, d=256, c=10, k=10, hubness="CSLS"),
     "c5": dict(n=1_000_000, m=10_000_000, d=128, c=50, k=10, hubness="LocalScaling"),
+    "c5dsl": dict(n=1_000_000, m=10_000_000, d=128, c=50, k=10, hubness="DisSimLocal"),
 }
 HUB_KWARGS = {"LocalScaling": {"method": "nicdm"}, "MutualProximity": {"method": "normal"}}
 ORACLE_HUB = {"CSLS": "csls", "LocalScaling": "nicdm", "MutualProximity": "mp_gaussian",

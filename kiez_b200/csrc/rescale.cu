@@ -493,6 +493,153 @@ row_stats_rg_kernel(const double *__restrict__ dist, int64_t n, int c, double *_
     }
 }
 
+// ---------------------------------------------------------------------------
+// narrow rows (c * nparts <= 16, e.g. kiez's default n_candidates = 10): ONE THREAD per row.
+// A 160-byte row does not feed a lane group: the 16-entry bitonic network of the row-group
+// path (shuffles of (double, int) pairs, NaN-aware compares) made those kernels instruction
+// bound at 0.14-0.20 of the HBM roofline.  Here a thread keeps its row in registers, orders it
+// with a branch-free rank sort on order-preserving 64-bit keys (C^2 integer compares, no
+// shuffles, no divergence) and scatters the k best straight to their final positions; a warp
+// covers 32 consecutive rows, so its loads and stores touch one contiguous span.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long sortable_bits(double v) {
+    if (isnan(v)) return ~0ull;                           // NaN last (numpy order), ties by position
+    const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+
+template <int C>
+__global__ void __launch_bounds__(128)
+rows_small_kernel(const RgParams p) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= p.n) return;
+    const int total = p.c * p.nparts;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    double x[C];
+    int64_t id[C];
+    double s = 0.0, sn = 0.0, cnt = 0.0;
+#pragma unroll
+    for (int e = 0; e < C; ++e) {
+        x[e] = qnan;
+        id[e] = -1;
+        if (e < total) {
+            const int part = e / p.c;
+            const int64_t off = (int64_t)part * p.part_stride + row * p.c + (e - part * p.c);
+            x[e] = p.dist[off];
+            id[e] = p.ind[off];
+            s += x[e];
+            if (!isnan(x[e])) { sn += x[e]; cnt += 1.0; }
+        }
+    }
+    double r[C];
+    if (p.op <= KB2_RESCALE_MP_GAUSS) {
+        const double mean = s / (double)p.c;                              // ndarray.mean
+        double mu = 0.0, sd = 0.0, last = 0.0;
+        if (p.op == KB2_RESCALE_LS) last = p.dist[row * p.c + p.c - 1];    // (same cache line)
+        if (p.op == KB2_RESCALE_MP_GAUSS) {                               // nanmean / nanstd(ddof=0)
+            mu = sn / cnt;
+            double q = 0.0;
+#pragma unroll
+            for (int e = 0; e < C; ++e)
+                if (!isnan(x[e])) { const double d = x[e] - mu; q += d * d; }
+            sd = sqrt(q / cnt);
+        }
+#pragma unroll
+        for (int e = 0; e < C; ++e) {
+            const bool ok = id[e] >= 0 && id[e] < p.n_stats;
+            const double a = ok ? __ldg(p.stat_a + id[e]) : qnan;
+            if (p.op == KB2_RESCALE_CSLS) {
+                r[e] = 2.0 * x[e] - mean - a;
+            } else if (p.op == KB2_RESCALE_LS) {
+                r[e] = 1.0 - exp(-1.0 * (x[e] * x[e]) / (last * a));
+            } else if (p.op == KB2_RESCALE_NICDM) {
+                r[e] = x[e] / sqrt(mean * a);
+            } else {
+                const double sb = ok ? __ldg(p.stat_b + id[e]) : qnan;
+                r[e] = 1.0 - norm_sf(x[e], mu, sd) * norm_sf(x[e], a, sb);
+            }
+        }
+    } else if (p.op == RG_OP_DSL_FINISH) {
+        const double mn = *p.gmin;
+        const double shift = (mn < 0.0) ? -mn : 0.0;
+#pragma unroll
+        for (int e = 0; e < C; ++e) {
+            const double v = x[e] + shift;
+            r[e] = p.squared ? v : sqrt(v);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < C; ++e) r[e] = x[e];
+    }
+    if (p.k == 0) {                                      // HubnessReduction.transform: unsorted
+#pragma unroll
+        for (int e = 0; e < C; ++e) {
+            if (e < total) {
+                p.out_dist[row * total + e] = r[e];
+                p.out_ind[row * total + e] = id[e];
+            }
+        }
+        return;
+    }
+    unsigned long long u[C];
+#pragma unroll
+    for (int e = 0; e < C; ++e) u[e] = (e < total) ? sortable_bits(r[e]) : ~0ull;
+#pragma unroll
+    for (int e = 0; e < C; ++e) {
+        if (e >= total) continue;
+        int rank = 0;                                    // entries ordered before e: (value, position)
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+            if (j == e) continue;
+            rank += (j < e) ? (u[j] <= u[e]) : (u[j] < u[e]);
+        }
+        if (rank < p.k) {
+            p.out_dist[row * p.k + rank] = r[e];
+            p.out_ind[row * p.k + rank] = id[e];
+        }
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(128)
+row_stats_small_kernel(const double *__restrict__ dist, int64_t n, int c, double *__restrict__ mean,
+                       double *__restrict__ sd, double *__restrict__ last) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    double x[C];
+    double s = 0.0, sn = 0.0, cnt = 0.0;
+#pragma unroll
+    for (int e = 0; e < C; ++e) {
+        x[e] = __longlong_as_double(0x7ff8000000000000LL);
+        if (e < c) {
+            x[e] = dist[row * c + e];
+            s += x[e];
+            if (!isnan(x[e])) { sn += x[e]; cnt += 1.0; }
+        }
+    }
+    const double lst = dist[row * c + c - 1];              // (same cache line)
+    const double mu = sn / cnt;
+    double q = 0.0;
+#pragma unroll
+    for (int e = 0; e < C; ++e)
+        if (!isnan(x[e])) { const double d = x[e] - mu; q += d * d; }
+    // `mean` serves CSLS/NICDM (plain mean) when sd == nullptr, MutualProximity otherwise
+    if (mean) mean[row] = sd ? mu : s / (double)c;
+    if (sd) sd[row] = sqrt(q / cnt);
+    if (last) last[row] = lst;
+}
+
+constexpr int SMALL_MAX_WIDTH = 16;
+static int launch_rows_small(const RgParams &p, cudaStream_t st) {
+    const int total = p.c * p.nparts;
+    const unsigned grid = (unsigned)ceil_div64(p.n, 128);
+    if (total <= 8) rows_small_kernel<8><<<grid, 128, 0, st>>>(p);
+    else if (total <= 12) rows_small_kernel<12><<<grid, 128, 0, st>>>(p);
+    else rows_small_kernel<16><<<grid, 128, 0, st>>>(p);
+    KB2_LAUNCH_CHECK();
+    return 0;
+}
+
 // dispatch on the row width: G lanes x E registers >= width
 template <template <int, int> class Launcher, class... Args>
 static int rg_dispatch(int width, Args... args) {
@@ -506,6 +653,7 @@ static int rg_dispatch(int width, Args... args) {
 template <int G, int E>
 struct RowsLauncher {
     static int run(const RgParams &p, cudaStream_t st) {
+        if (p.c * p.nparts <= SMALL_MAX_WIDTH) return launch_rows_small(p, st);
         const int64_t rows_per_block = (int64_t)RG_WARPS * (32 / G);
         rows_rg_kernel<G, E><<<(unsigned)ceil_div64(p.n, rows_per_block), RG_WARPS * 32, 0, st>>>(p);
         KB2_LAUNCH_CHECK();
@@ -516,6 +664,14 @@ template <int G, int E>
 struct StatsLauncher {
     static int run(const double *dist, int64_t n, int c, double *mean, double *sd, double *last,
                    cudaStream_t st) {
+        if (c <= SMALL_MAX_WIDTH) {
+            const unsigned grid = (unsigned)ceil_div64(n, 128);
+            if (c <= 8) row_stats_small_kernel<8><<<grid, 128, 0, st>>>(dist, n, c, mean, sd, last);
+            else if (c <= 12) row_stats_small_kernel<12><<<grid, 128, 0, st>>>(dist, n, c, mean, sd, last);
+            else row_stats_small_kernel<16><<<grid, 128, 0, st>>>(dist, n, c, mean, sd, last);
+            KB2_LAUNCH_CHECK();
+            return 0;
+        }
         const int64_t rows_per_block = (int64_t)RG_WARPS * (32 / G);
         row_stats_rg_kernel<G, E><<<(unsigned)ceil_div64(n, rows_per_block), RG_WARPS * 32, 0, st>>>(
             dist, n, c, mean, sd, last);

@@ -33,7 +33,14 @@ def shard_bounds(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def upload_sharded(data, device, group=None) -> torch.Tensor:
+def shard_slice(n_rows: int, group=None) -> Tuple[int, int, int]:
+    """(lo, hi, per): the rows this rank uploads of a host matrix every rank holds."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    per = -(-n_rows // world)
+    return min(n_rows, rank * per), min(n_rows, (rank + 1) * per), per
+
+
+def upload_sharded(data, device, group=None, mine=None) -> torch.Tensor:
     """A host matrix every rank holds (numpy or CPU tensor, fp32 / fp64 kept, anything else ->
     fp32) -> the full matrix on `device`, moving only 1/world of it over this rank's
     host-to-device link: rank r uploads rows [r * per, (r + 1) * per), per = ceil(n / world), and
@@ -41,22 +48,25 @@ def upload_sharded(data, device, group=None) -> torch.Tensor:
     run it with device = "cpu"."""
     import numpy as np
 
-    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    world = dist.get_world_size(group)
     n, d = data.shape
-    per = -(-n // world)
-    lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
+    lo, hi, per = shard_slice(n, group)
     if isinstance(data, np.ndarray):
         dtype = torch.float64 if data.dtype == np.float64 else torch.float32
-        part = torch.from_numpy(np.ascontiguousarray(
-            data[lo:hi], dtype=np.float64 if dtype == torch.float64 else np.float32))
     else:
         dtype = torch.float64 if data.dtype == torch.float64 else torch.float32
-        part = data[lo:hi].to(dtype).contiguous()
     full = torch.empty((world * per, d), dtype=dtype, device=device)
     # the last rank's slice may be short: the padding rows are never read (full[:n])
-    mine = torch.zeros((per, d), dtype=dtype, device=device)
-    mine[: hi - lo].copy_(part, non_blocking=True)
-    dist.all_gather_into_tensor(full, mine, group=group)
+    padded = torch.zeros((per, d), dtype=dtype, device=device)
+    if mine is not None:         # the slice is on the device already (overlapped upload, fp32)
+        padded[: hi - lo].copy_(mine)
+    elif isinstance(data, np.ndarray):
+        padded[: hi - lo].copy_(torch.from_numpy(np.ascontiguousarray(
+            data[lo:hi], dtype=np.float64 if dtype == torch.float64 else np.float32)),
+            non_blocking=True)
+    else:
+        padded[: hi - lo].copy_(data[lo:hi].to(dtype).contiguous(), non_blocking=True)
+    dist.all_gather_into_tensor(full, padded, group=group)
     return full[:n]
 
 
@@ -152,6 +162,57 @@ def sharded_knn_both(algo, rows, cols, k_fwd: int, k_rev: int, exclude_self_rows
     return fwd, (rev_d, rev_i)
 
 
+def all_gather_blocks(d, i, total: int, per: int, bounds, group=None):
+    """Per-rank result blocks (rows bounds(r) of the full result, at most `per` each; d float64,
+    i int64, same shape) -> the full (total, k) result on every rank: one packed all-gather
+    (dist bits | ind)."""
+    world = dist.get_world_size(group)
+    k = d.shape[1]
+    n_loc = d.shape[0]
+    packed = torch.zeros(2 * per * k, dtype=torch.int64, device=d.device)
+    packed[: n_loc * k] = d.contiguous().view(torch.int64).reshape(-1)
+    packed[per * k: per * k + n_loc * k] = i.reshape(-1)
+    gathered = torch.empty(world * 2 * per * k, dtype=torch.int64, device=d.device)
+    dist.all_gather_into_tensor(gathered, packed, group=group)
+    g = gathered.view(world, 2, per, k)
+    out_d = torch.empty((total, k), dtype=torch.float64, device=d.device)
+    out_i = torch.empty((total, k), dtype=torch.int64, device=d.device)
+    for r in range(world):
+        lo, hi = bounds(r)
+        out_d[lo:hi] = g[r, 0, : hi - lo].view(torch.float64)
+        out_i[lo:hi] = g[r, 1, : hi - lo]
+    return out_d, out_i
+
+
+def dsl_transform_sharded(n: int, raw_fn, finish_fn, group=None):
+    """DisSimLocal.transform with the QUERY rows sharded (dis_sim.py:139-181): rank r computes the
+    raw values of its rows -- raw_fn(lo, hi) -> (raw, ind, local_min) --, the ranks agree on the
+    GLOBAL minimum of the whole (n, c) matrix with one all-reduce(MIN) (dis_sim.py:171-173 shifts
+    by it), finish_fn(raw, ind, global_min) -> (dist, ind) of the own rows, and one all-gather
+    replicates the result.  Backend-agnostic (the gloo test injects numpy)."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = shard_bounds(n, world, rank)
+    raw, ind, gmin = raw_fn(lo, hi)
+    dist.all_reduce(gmin, op=dist.ReduceOp.MIN, group=group)
+    d, i = finish_fn(raw, ind, gmin)
+    return all_gather_blocks(d, i, n, -(-n // world), lambda r: shard_bounds(n, world, r), group)
+
+
+def all_gather_vector(x_local, total: int, group=None):
+    """Concatenate per-rank 1-d float64 shards (rank r holds shard_bounds(total, world, r))."""
+    world = dist.get_world_size(group)
+    per = -(-total // world)
+    mine = torch.zeros(per, dtype=x_local.dtype, device=x_local.device)
+    mine[: x_local.numel()] = x_local
+    gathered = torch.empty(world * per, dtype=x_local.dtype, device=x_local.device)
+    dist.all_gather_into_tensor(gathered, mine, group=group)
+    out = torch.empty(total, dtype=x_local.dtype, device=x_local.device)
+    for r in range(world):
+        lo, hi = shard_bounds(total, world, r)
+        out[lo:hi] = gathered[r * per: r * per + hi - lo]
+    return out
+
+
 class RowShardComm:
     """The collectives of the row-sharded dual-direction pass (`B200.search_both(comm=...)`).
 
@@ -213,6 +274,15 @@ class RowShardComm:
         per = -(-m // self.world)
         return min(m, self.rank * per), min(m, (self.rank + 1) * per), per
 
+    def gather_columns(self, x_local, m: int):
+        """Per-column values of this rank's column shard (`column_shard(m)`) -> all m on every rank."""
+        _c0, _c1, per = self.column_shard(m)
+        mine = torch.zeros(per, dtype=x_local.dtype, device=x_local.device)
+        mine[: x_local.numel()] = x_local
+        gathered = torch.empty(self.world * per, dtype=x_local.dtype, device=x_local.device)
+        dist.all_gather_into_tensor(gathered, mine, group=self.group)
+        return gathered[:m].contiguous()
+
     def columns_to_owners(self, heads, pad_value):
         """heads [m][cap] int64 (this rank's best rows per column) -> (recv [world][per][cap]:
         the heads of this rank's column shard from every rank, c0, c1).  One all-to-all."""
@@ -227,23 +297,7 @@ class RowShardComm:
         return recv, c0, c1
 
     def gather_blocks(self, d, i, total: int, per: int, bounds):
-        """Per-rank result blocks (rows bounds(r) of the full result, at most `per` each) ->
-        the full (total, k) result on every rank: one packed all-gather (dist bits | ind)."""
-        k = d.shape[1]
-        n_loc = d.shape[0]
-        packed = torch.zeros(2 * per * k, dtype=torch.int64, device=d.device)
-        packed[: n_loc * k] = d.contiguous().view(torch.int64).reshape(-1)
-        packed[per * k: per * k + n_loc * k] = i.reshape(-1)
-        gathered = torch.empty(self.world * 2 * per * k, dtype=torch.int64, device=d.device)
-        dist.all_gather_into_tensor(gathered, packed, group=self.group)
-        g = gathered.view(self.world, 2, per, k)
-        out_d = torch.empty((total, k), dtype=torch.float64, device=d.device)
-        out_i = torch.empty((total, k), dtype=torch.int64, device=d.device)
-        for r in range(self.world):
-            lo, hi = bounds(r)
-            out_d[lo:hi] = g[r, 0, : hi - lo].view(torch.float64)
-            out_i[lo:hi] = g[r, 1, : hi - lo]
-        return out_d, out_i
+        return all_gather_blocks(d, i, total, per, bounds, self.group)
 
 
 def sharded_knn_both_rows(algo, rows, cols, k_fwd: int, k_rev: int, exclude_self_rows: bool,

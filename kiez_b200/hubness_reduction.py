@@ -375,12 +375,25 @@ class DisSimLocal(HubnessReduction):
         ri = _as_device(neigh_ind, dev, torch.int64)
         m, c_rev = ri.shape
         d = src.shape[1]
+        # multi-GPU: every rank fits a shard of the target rows (the centroid gathers are the
+        # heavy part: m * c * d * 4 bytes) and the per-target scalars are all-gathered; the
+        # centroids themselves stay sharded (`target_centroids_` = this rank's rows)
+        lo, hi = 0, m
+        if self._sharded():
+            from .distributed import shard_bounds
+
+            lo, hi = shard_bounds(m, torch.distributed.get_world_size(), torch.distributed.get_rank())
         with torch.cuda.device(dev):
-            cent = torch.empty((m, d), dtype=torch.float64, device=dev)
-            d2c = torch.empty(m, dtype=torch.float64, device=dev)
-            lib.call("kb2_dsl_fit", lib.ptr(src), src.shape[0], src.stride(0), lib.ptr(tgt), m,
-                     tgt.stride(0), d, src.element_size(), lib.ptr(ri), c_rev, lib.ptr(cent),
-                     lib.ptr(d2c), lib.stream_ptr())
+            cent = torch.empty((hi - lo, d), dtype=torch.float64, device=dev)
+            d2c = torch.empty(hi - lo, dtype=torch.float64, device=dev)
+            if hi > lo:
+                lib.call("kb2_dsl_fit", lib.ptr(src), src.shape[0], src.stride(0), lib.ptr(tgt[lo:hi]),
+                         hi - lo, tgt.stride(0), d, src.element_size(), lib.ptr(ri[lo:hi]), c_rev,
+                         lib.ptr(cent), lib.ptr(d2c), lib.stream_ptr())
+        if self._sharded():
+            from .distributed import all_gather_vector
+
+            d2c = all_gather_vector(d2c, m)
         self.source_ = source
         self.target_ = target
         self._target_dev = tgt
@@ -388,7 +401,12 @@ class DisSimLocal(HubnessReduction):
         self.target_dist_to_centroids_ = d2c
         return self
 
-    def _raw(self, neigh_ind, query):
+    def _sharded(self) -> bool:
+        """Row-sharded rescale: a distributed backend replicates the kNN results on every rank."""
+        return bool(getattr(self.nn_algo, "distributed", False)) and \
+            torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
+
+    def _raw(self, neigh_ind, query, lo=0, hi=None):
         lib = _lib()
         algo = self.nn_algo
         dev = _device_of(algo)
@@ -397,15 +415,30 @@ class DisSimLocal(HubnessReduction):
         if q.dtype != tgt.dtype:
             q = q.to(tgt.dtype)
         i = _as_device(neigh_ind, dev, torch.int64)
+        if hi is not None:
+            q, i = q[lo:hi], i[lo:hi].contiguous()
         n, c = i.shape
         with torch.cuda.device(dev):
             raw = torch.empty((n, c), dtype=torch.float64, device=dev)
             gmin = torch.full((1,), float("inf"), dtype=torch.float64, device=dev)
-            lib.call("kb2_dsl_transform", lib.ptr(q), n, q.stride(0), lib.ptr(tgt), tgt.shape[0],
-                     tgt.stride(0), q.shape[1], q.element_size(), lib.ptr(i), c,
-                     lib.ptr(self.target_dist_to_centroids_), lib.ptr(raw), lib.ptr(gmin),
-                     lib.stream_ptr())
+            if n:
+                lib.call("kb2_dsl_transform", lib.ptr(q), n, q.stride(0), lib.ptr(tgt), tgt.shape[0],
+                         tgt.stride(0), q.shape[1], q.element_size(), lib.ptr(i), c,
+                         lib.ptr(self.target_dist_to_centroids_), lib.ptr(raw), lib.ptr(gmin),
+                         lib.stream_ptr())
         return raw, i, gmin
+
+    def _run(self, neigh_ind, query, k):
+        """Both stages; with a distributed backend the query rows are sharded and the global
+        minimum (dis_sim.py:171-173) is agreed with one all-reduce(MIN)."""
+        if not self._sharded():
+            raw, i, gmin = self._raw(neigh_ind, query)
+            return self._finish_topk(raw, i, gmin, k)
+        from .distributed import dsl_transform_sharded
+
+        return dsl_transform_sharded(
+            neigh_ind.shape[0], lambda lo, hi: self._raw(neigh_ind, query, lo, hi),
+            lambda raw, i, gmin: self._finish_topk(raw, i, gmin, k))
 
     def _finish_topk(self, raw, i, gmin, k):
         lib = _lib()
@@ -415,16 +448,15 @@ class DisSimLocal(HubnessReduction):
         with torch.cuda.device(dev):
             od = torch.empty((n, width), dtype=torch.float64, device=dev)
             oi = torch.empty((n, width), dtype=torch.int64, device=dev)
-            lib.call("kb2_dsl_finish_topk", lib.ptr(raw), lib.ptr(i), n, c, lib.ptr(gmin),
-                     int(bool(self.squared)), k, lib.ptr(od), lib.ptr(oi), lib.stream_ptr())
+            if n:
+                lib.call("kb2_dsl_finish_topk", lib.ptr(raw), lib.ptr(i), n, c, lib.ptr(gmin),
+                         int(bool(self.squared)), k, lib.ptr(od), lib.ptr(oi), lib.stream_ptr())
         return od, oi
 
     def transform(self, neigh_dist, neigh_ind, query):
         check_is_fitted(self, ["target_", "target_centroids_", "target_dist_to_centroids_"])
-        raw, i, gmin = self._raw(neigh_ind, query)     # neigh_dist is ignored (dis_sim.py:152-157)
-        return self._finish_topk(raw, i, gmin, 0)
+        return self._run(neigh_ind, query, 0)          # neigh_dist is ignored (dis_sim.py:152-157)
 
     def _transform_topk(self, neigh_dist, neigh_ind, query, k):
         check_is_fitted(self, ["target_", "target_centroids_", "target_dist_to_centroids_"])
-        raw, i, gmin = self._raw(neigh_ind, query)
-        return self._finish_topk(raw, i, gmin, min(k, raw.shape[1]))
+        return self._run(neigh_ind, query, min(k, neigh_ind.shape[1]))

@@ -341,7 +341,27 @@ class B200Mixin:
 
         self._uploader = None
         self._pending_uploads = {}
-        if self.distributed or os.environ.get("KB2_ASYNC_UPLOAD", "1") == "0":
+        if os.environ.get("KB2_ASYNC_UPLOAD", "1") == "0":
+            return
+        if self.distributed:
+            # every rank uploads its 1 / world slice of each host matrix (the all-gather over
+            # NVLink completes it, distributed.upload_sharded): start both slices now, through
+            # the pinned staging ring, so that the copies overlap each other and the first kernels
+            from .distributed import shard_slice
+
+            up = upload.Uploader()
+            with torch.cuda.device(self.device):
+                for m in ((source, target) if not only_fit_target else (target,)):
+                    if m is None or not upload.eligible(m) or m.shape[0] < 4096 or \
+                            ("slice", id(m)) in self._pending_uploads:
+                        continue
+                    lo, hi, _per = shard_slice(m.shape[0])
+                    if hi > lo:
+                        self._pending_uploads[("slice", id(m))] = up.add(
+                            upload.HostUpload(m[lo:hi], self.device))
+            if up.jobs:
+                up.start()
+                self._uploader = up
             return
         mats = [m for m in ((target, source) if not only_fit_target else (target,))
                 if m is not None and upload.eligible(m)
@@ -439,7 +459,14 @@ class B200Mixin:
     def _upload_sharded(self, data):
         from .distributed import upload_sharded
 
-        return upload_sharded(data, self.device)
+        job = getattr(self, "_pending_uploads", {}).pop(("slice", id(data)), None)
+        mine = None
+        if job is not None:                      # this rank's slice is (being) uploaded already
+            stream = torch.cuda.current_stream(self.device)
+            for chunk in range(len(job.bounds)):
+                job.wait(chunk, stream)
+            mine = job.dev
+        return upload_sharded(data, self.device, mine=mine)
 
     def _prepare(self, data, cache: bool, lazy: bool = False) -> PreparedRows:
         """The prepared operands of `data` (cached per fitted matrix).  `lazy`: a matrix whose
@@ -578,7 +605,12 @@ class B200Mixin:
         if self.precision != "auto":
             return True
         if self._screen_ok is None:
-            frac = float(unverified.to(torch.float32).mean()) if unverified.numel() else 0.0
+            if unverified is None:
+                frac = 0.0
+            elif unverified.dim() == 0:                    # a fraction from _probe_fraction
+                frac = float(unverified)
+            else:
+                frac = float(unverified.to(torch.float32).mean()) if unverified.numel() else 0.0
             if comm is not None:
                 frac = comm.max_scalar(frac)       # every rank must take the same branch
             self.search_stats.setdefault("screen_probe_unverified", []).append(frac)
@@ -590,6 +622,36 @@ class B200Mixin:
                 return False
             self._screen_ok = frac <= self.SCREEN_MAX_UNVERIFIED
         return self._screen_ok
+
+    def _probe_fraction(self, unverified, q: PreparedRows, y: PreparedRows, keys, lists: int,
+                        cap: int, out_d, k: int):
+        """Fraction of the probe rows a SINGLE list of `cap` entries would leave unproven (device
+        scalar).  A probe over few query tiles searches the index in `lists` independent ranges;
+        the proof then runs with tau = min over the lists' cap-th keys, about the (lists * cap)-th
+        best key overall -- far easier to pass than the cap-th best that the chained launches
+        of the rest of the fit (and the column side) prove against.  So the verdict is taken
+        on what those would see: tau_1 = cap-th smallest key of the union of the lists."""
+        if lists <= 1 or unverified.numel() == 0:
+            return unverified.to(torch.float32).mean() if unverified.numel() else \
+                torch.zeros((), device=self.device)
+        lib = self._lib
+        tau1 = torch.kthvalue(keys.view(q.n, lists * cap), cap, dim=1).values.double()
+        up = 1.000001
+        cosine = self._metric_code == lib.METRIC_COSINE
+        one = torch.ones((), dtype=torch.float64, device=self.device)
+        qn2 = one.expand(q.n) if cosine else q.key.double()
+        ym2 = one if cosine else y.keymax.double()
+        qn, ym = qn2.sqrt() * up, ym2.sqrt() * up
+        dq, dym = q.err.double().sqrt() * up, y.errmax.double().sqrt() * up
+        E = 2.0 * (dq * ym + qn * (1.0 + 2.0 ** -11) * dym + self._eps_acc(q.dpad) * qn * ym) \
+            + 4.76837158203125e-07 * (ym2 + 2.0 * qn * ym)
+        kd = out_d[:, k - 1]
+        if cosine:
+            ok = 2.0 * (kd - 1.0) + 1e-9 < tau1 - E - 1e-6
+        else:
+            d2 = kd * kd if self._metric_code == lib.METRIC_EUCLIDEAN else kd
+            ok = d2 * (1.0 + 1e-12) < tau1 - E + qn2 * (1.0 - 2.4e-7)
+        return 1.0 - (ok | torch.isinf(tau1)).to(torch.float32).mean()
 
     def _eps_acc(self, dpad: int) -> float:
         """Bound of the accumulation error of <hi(q), hi(y)> relative to |q| |y|: the TF32
@@ -698,18 +760,20 @@ class B200Mixin:
             return False
         if self.fused is True:
             return True
-        # auto: only where the pass is tensor-bound (measured: with d = 128 the doubled epilogue
-        # is the limiter and two passes are faster; at d = 256 the pass wins for every list
-        # length it takes: C4 at c = 50 runs 1388 ms against 2165 ms for two screen passes),
-        # and only for problems large enough to amortise the threshold sample
-        if rows.dpad < 192 or rows.n * cols.n < (1 << 32):
+        # auto: where the pass beats two one-direction passes (measured with the 1xTF32 screen:
+        # C4 at c = 50 runs 1388 ms against 2165 ms, C5 -- d = 128, c = 50, 10 M columns --
+        # 8.07 s against 10.13 s), and only for problems large enough to amortise the
+        # threshold sample
+        if rows.dpad < 128 or rows.n * cols.n < (1 << 32):
             return False
         # the column buffers must fit; decided from rank-independent quantities only (shapes,
         # world size, the device's TOTAL memory) so that every rank of a distributed run takes
         # the same branch -- the branches issue different collectives
         world = torch.distributed.get_world_size() if self.distributed else 1
+        if self.distributed and self.shard_mode == "rows":
+            world = 1                               # every rank buffers all columns
         total = torch.cuda.get_device_properties(self.device).total_memory
-        return (cols.n // world + 1) * self._fused_col_cap(cap) * 8 < 0.2 * total
+        return (cols.n // world + 1) * self._fused_col_cap(cap) * 8 < 0.3 * total
 
     def _fused_col_cap(self, cap: int) -> int:
         return max(self.FUSED_COL_CAP, cap)
@@ -758,33 +822,46 @@ class B200Mixin:
             #    uploaded sent exactly these rows ahead, see _start_uploads); with sharded rows
             #    every rank searches its share of the sample
             n_s_total = self._fused_sample_rows(n_total, cap)
-            n_s = n_s_total if comm is None else max(1, min(n_total // world, -(-n_s_total // world)))
-            step = max(1, rows.n // n_s)
-            if rows.presample is not None and rows.presample[0] == (n_s, step):
-                sample = rows.presample[1].ensure()
+            n_s = n_s_total
+            if comm is None:
+                step = max(1, rows.n // n_s)
+                if rows.presample is not None and rows.presample[0] == (n_s, step):
+                    sample = rows.presample[1].ensure()
+                else:
+                    sample = rows.take(torch.arange(n_s, device=dev, dtype=torch.int64) * step)
+                s_cols = cols
             else:
-                sample = rows.take(torch.arange(n_s, device=dev, dtype=torch.int64) * step)
-            if screen and self._use_screen(cols, sample, cap, dual=False):
-                _s_idx, s_key, lists = self._screen_search(cols, sample, cap)
+                # the sample comes from ALL rows (every rank holds them); each rank searches it
+                # for a shard of the columns, so the pass costs 1 / world of the single-GPU one
+                # and yields the very same thresholds
+                step = max(1, n_total // n_s)
+                sample = comm.rows_full.take(torch.arange(n_s, device=dev, dtype=torch.int64) * step)
+                sc0, sc1, _per = comm.column_shard(cols.n)
+                s_cols = cols.rows(sc0, sc1) if sc1 > sc0 else None
+            if s_cols is None:
+                tau = torch.empty((0,), dtype=torch.float32, device=dev)
+                s_key = _s_idx = None
+            elif screen and self._use_screen(s_cols, sample, cap, dual=False):
+                _s_idx, s_key, lists = self._screen_search(s_cols, sample, cap)
             else:
-                lists = lib.lib.kb2_suggest_splits(cols.n, n_s, cap, sm)
-                _s_idx = torch.empty((cols.n, lists * cap), dtype=torch.int32, device=dev)
-                s_key = torch.empty((cols.n, lists * cap), dtype=torch.float32, device=dev)
+                lists = lib.lib.kb2_suggest_splits(s_cols.n, n_s, cap, sm)
+                _s_idx = torch.empty((s_cols.n, lists * cap), dtype=torch.int32, device=dev)
+                s_key = torch.empty((s_cols.n, lists * cap), dtype=torch.float32, device=dev)
                 if prof is not None:
                     ev0 = torch.cuda.Event(enable_timing=True)
                     ev0.record()
-                lib.call("kb2_knn_candidates", lib.KNN_AUTO, lib.ptr(cols.hi), lib.ptr(cols.lo), cols.n,
-                         lib.ptr(sample.hi), lib.ptr(sample.lo), lib.ptr(sample.key), n_s, rows.dpad,
-                         cap, lists, lib.ptr(_s_idx), lib.ptr(s_key), st)
+                lib.call("kb2_knn_candidates", lib.KNN_AUTO, lib.ptr(s_cols.hi), lib.ptr(s_cols.lo),
+                         s_cols.n, lib.ptr(sample.hi), lib.ptr(sample.lo), lib.ptr(sample.key), n_s,
+                         rows.dpad, cap, lists, lib.ptr(_s_idx), lib.ptr(s_key), st)
                 if prof is not None:
                     ev1 = torch.cuda.Event(enable_timing=True)
                     ev1.record()
-                    prof.append((ev0, ev1, cols.n, n_s, rows.d, "tf32x3"))
+                    prof.append((ev0, ev1, s_cols.n, n_s, rows.d, "tf32x3"))
             # the cap-th best within ANY subset of the rows bounds the final cap-th best
-            if comm is None:
-                tau = s_key.view(cols.n, lists, cap)[:, :, cap - 1].amin(dim=1).contiguous()
-            else:
-                tau = comm.kth_over_ranks(s_key, cap)      # cap-th best over the ranks' samples
+            if s_key is not None:
+                tau = s_key.view(s_cols.n, lists, cap)[:, :, cap - 1].amin(dim=1).contiguous()
+            if comm is not None:
+                tau = comm.gather_columns(tau, cols.n)
             del _s_idx, s_key, sample
             # 2. the dual-direction pass, one launch per row segment; exact finish of the row
             #    lists per segment; thresholds tighten between segments
@@ -804,6 +881,7 @@ class B200Mixin:
             # statistics for bench.py / tests (extra reductions and host syncs): only on request
             stats = bool(getattr(self, "_collect_stats", False))
             emitted = torch.zeros((), dtype=torch.int64, device=dev) if stats else None
+            probe = None
             for s_no, (lo, hi) in enumerate(zip(bounds[:-1], bounds[1:])):
                 last = s_no == len(bounds) - 2
                 seg = rows.rows(lo, hi) if hi > lo else None
@@ -815,6 +893,9 @@ class B200Mixin:
                     self._refine_checked(seg, cols, cand_rows, k_rows, exclude_self_rows,
                                          lib.ptr(key_rows) + 4 * (cap - 1), r_lists * cap, cap, r_lists,
                                          out=(fwd_d[lo:hi], fwd_i[lo:hi], unv_rows[lo:hi]))
+                    if s_no == 0 and self._screen_ok is None:
+                        probe = self._probe_fraction(unv_rows[lo:hi], seg, cols, key_rows, r_lists, cap,
+                                                     fwd_d[lo:hi], k_rows)
                     del key_rows, cand_rows
                 else:
                     splits = lib.lib.kb2_suggest_splits(seg.n, cols.n, cap, sm)
@@ -834,7 +915,7 @@ class B200Mixin:
                                  out=(fwd_d[lo:hi], fwd_i[lo:hi]))
                     del cand_rows
                 if screen and s_no == 0 and len(bounds) > 2 and not self._screen_verdict(
-                        unv_rows[lo:hi], cap, rows.dpad, dual=True, comm=comm):
+                        probe if seg is not None else None, cap, rows.dpad, dual=True, comm=comm):
                     # probe failed: start over with longer lists, or with 3xTF32 keys
                     # (_capacity / _use_screen now answer differently)
                     del col_buf, col_cnt, fwd_d, fwd_i, unv_rows, tau
@@ -987,8 +1068,11 @@ class B200Mixin:
                 self._refine_checked(part, y, cand, k, exclude_self, lib.ptr(ckey) + 4 * (cap - 1),
                                      lists * cap, cap, lists,
                                      out=(out_d[lo:hi], out_i[lo:hi], unv[lo:hi]))
+                probe = None
+                if len(parts) > 1 and lo == 0 and self._screen_ok is None:
+                    probe = self._probe_fraction(unv[lo:hi], part, y, ckey, lists, cap, out_d[lo:hi], k)
                 del cand, ckey
-                if len(parts) > 1 and lo == 0 and not self._screen_verdict(unv[lo:hi], cap, q.dpad) \
+                if len(parts) > 1 and lo == 0 and not self._screen_verdict(probe, cap, q.dpad) \
                         and self._screen_ok is None:
                     # the probe asks for longer lists: start over (3xTF32 verdicts carry on below)
                     del out_d, out_i, unv

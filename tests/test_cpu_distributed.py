@@ -225,21 +225,33 @@ class _RowShardOracleAlgo:
             d[r[ok], c[ok]] = np.inf
         order = np.argsort(d, axis=1, kind="stable")[:, :k_rows]
         fwd = (torch.from_numpy(np.take_along_axis(d, order, 1)), torch.from_numpy(order + cols.base))
-        # thresholds: every rank's best keys against its share of the sample, kth over the ranks
-        n_s = max(1, rows.n // 3)
-        s_keys = np.full((cols.n, cap), np.inf, dtype=np.float32)
-        srt = np.sort(key[:n_s].T, axis=1)[:, :cap]
-        s_keys[:, : srt.shape[1]] = srt
-        tau = comm.kth_over_ranks(torch.from_numpy(s_keys), cap)
-        # emits strictly below the threshold; the best cap of them are the column's head
-        heads = np.full((cols.n, cap), EMPTY, dtype=np.int64)
+        # thresholds: the sample comes from ALL rows; every rank searches it for its column shard
+        full = comm.rows_full.x
+        sample = full[:: max(1, full.shape[0] // max(cap, full.shape[0] // 3))]
+        c0s, c1s, _per = comm.column_shard(cols.n)
+        s_key = O._pairwise(cols.x[c0s:c1s], sample, "sqeuclidean").astype(np.float32)
+        tau_loc = np.sort(s_key, axis=1)[:, min(cap, s_key.shape[1]) - 1] if c1s > c0s else np.zeros(0, np.float32)
+        tau = comm.gather_columns(torch.from_numpy(np.ascontiguousarray(tau_loc, dtype=np.float32)), cols.n)
+        # two row segments: emits strictly below the threshold, the best cap of them are the
+        # column's head; between the segments the ranks agree on the cap-th best key so far
         bound = tau.numpy().copy()
+        kept = [np.zeros(0, dtype=np.int64) for _ in range(cols.n)]
+        half = rows.n // 2
+        for seg_no, (lo, hi) in enumerate(((0, half), (half, rows.n))):
+            keys = np.full((cols.n, cap), np.inf, dtype=np.float32)
+            for c in range(cols.n):
+                hit = lo + np.flatnonzero(key[lo:hi, c] < bound[c])
+                cand = np.concatenate([kept[c], hit])
+                kept[c] = cand[np.argsort(key[cand, c], kind="stable")][:cap]
+                if len(cand) >= cap:
+                    bound[c] = key[kept[c][-1], c]
+                keys[c, : len(kept[c])] = key[kept[c], c]
+            if seg_no == 0:
+                t = comm.kth_over_ranks(torch.from_numpy(keys), cap, tau=torch.from_numpy(bound.copy()))
+                bound = t.numpy().copy()
+        heads = np.full((cols.n, cap), EMPTY, dtype=np.int64)
         for c in range(cols.n):
-            hit = np.flatnonzero(key[:, c] < bound[c])
-            best = hit[np.argsort(key[hit, c], kind="stable")][:cap]
-            heads[c, : len(best)] = _pack(key[best, c], best + rows.base)
-            if len(hit) >= cap:
-                bound[c] = key[best[-1], c]
+            heads[c, : len(kept[c])] = _pack(key[kept[c], c], kept[c] + rows.base)
         tau = comm.min_(torch.from_numpy(bound))
         recv, c0, c1 = comm.columns_to_owners(torch.from_numpy(heads), int(EMPTY))
         merged = recv.numpy().transpose(1, 0, 2)[: c1 - c0].reshape(c1 - c0, -1)
@@ -247,7 +259,6 @@ class _RowShardOracleAlgo:
         ids = (merged & np.uint64(0xFFFFFFFF)).astype(np.int64)
         ids[ids == 0xFFFFFFFF] = -1
         # exact finish of the owner's columns against ALL rows
-        full = comm.rows_full.x
         rd = np.full((c1 - c0, k_cols), np.inf)
         ri = np.full((c1 - c0, k_cols), -1, dtype=np.int64)
         for j in range(c1 - c0):
@@ -290,3 +301,60 @@ def test_sharded_knn_both_rows_gloo(nx, ny, k, single, world):
         assert fd.shape == (nx, k) and rd.shape == (y.shape[0], k)
         O.assert_neighbors_match(fd, fi, want_fd, want_fi, 1e-9, 1e-9, what=f"rows fwd rank{rank}")
         O.assert_neighbors_match(rd, ri, want_rd, want_ri, 1e-9, 1e-9, what=f"rows rev rank{rank}")
+
+
+def _dsl_worker(rank, world, port, source, target, fwd_i, rev_i, k, squared, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from kiez_b200.distributed import all_gather_vector, dsl_transform_sharded
+
+        m, n = target.shape[0], source.shape[0]
+        # _fit sharded over the target rows: per-target scalars all-gathered
+        t0, t1 = shard_bounds(m, world, rank)
+        cent = source[rev_i[t0:t1]].mean(axis=1)
+        d2c = all_gather_vector(torch.from_numpy(((target[t0:t1] - cent) ** 2).sum(axis=1)), m).numpy()
+
+        def raw_fn(lo, hi):
+            q, ind = source[lo:hi], fwd_i[lo:hi]
+            sq = ((q[:, None, :] - target[ind]) ** 2).sum(axis=2)
+            qc = ((q - target[ind].mean(axis=1)) ** 2).sum(axis=1)
+            raw = sq - qc[:, None] - d2c[ind]
+            gmin = torch.tensor([raw.min() if raw.size else np.inf], dtype=torch.float64)
+            return raw, ind, gmin
+
+        def finish_fn(raw, ind, gmin):
+            v = raw + (-float(gmin) if float(gmin) < 0 else 0.0)
+            v = v if squared else np.sqrt(v)
+            d, i = O.sort_topk(v, ind, k)
+            return torch.from_numpy(d), torch.from_numpy(i)
+
+        d, i = dsl_transform_sharded(n, raw_fn, finish_fn)
+        out[rank] = (d.numpy(), i.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize(("n", "m", "world", "squared"), [(41, 30, 2, False), (7, 9, 3, True)])
+def test_dsl_global_minimum_all_reduce_gloo(n, m, world, squared):
+    """DisSimLocal with sharded rows: the shift is the minimum of the WHOLE (n, c) matrix
+    (dis_sim.py:171-173), so the ranks all-reduce(MIN) their local minima between the two stages;
+    the result must equal the oracle's single-process transform on every rank."""
+    rng = np.random.default_rng(n * m)
+    source, target = rng.standard_normal((n, 5)), rng.standard_normal((m, 5))
+    c, k = 4, 3
+    _fd, fwd_i = O.knn_brute(source, target, c)
+    _rd, rev_i = O.knn_brute(target, source, c)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_dsl_worker, args=(world, _free_port(), source, target, fwd_i, rev_i, k, squared, out),
+             nprocs=world, join=True)
+    want = O.dsl_transform(fwd_i, source, target, O.dsl_fit(rev_i, source, target)[1], squared=squared)
+    want_d, want_i = O.sort_topk(want, fwd_i, k)
+    local_mins = []
+    for rank in range(world):
+        lo, hi = shard_bounds(n, world, rank)
+        local_mins.append(want[lo:hi].min() if hi > lo else np.inf)
+        d, i = out[rank]
+        O.assert_neighbors_match(d, i, want_d, want_i, 1e-9, 1e-9, what=f"dsl rank{rank}")
+    assert len(set(np.round(local_mins, 9))) > 1      # the shards really disagree on their minimum
