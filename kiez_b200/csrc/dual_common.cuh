@@ -95,16 +95,16 @@ __device__ __forceinline__ void column_tile(const FusedParams &FP, EmitQueue &Q,
     constexpr int NCH = BN / 32;
     const float nxk = -xk;
     auto process = [&](const uint32_t (&r)[32], int ch) {
-        // g = -2 acc - tau_col;  emit when  key_x - 2 acc < tau_col  <=>  g < -key_x
-        float g[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) g[j] = fmaf(-2.f, __uint_as_float(r[j]), -tk[ch * 32 + j]);
+        // g = -2 acc - tau_col;  emit when  key_x - 2 acc < tau_col  <=>  g < -key_x.  The g are
+        // not kept (they are recomputed on the rare slow path): the accumulator registers of the
+        // chunk stay the only 32-wide array that is live across the test.
+        auto gval = [&](int j) { return fmaf(-2.f, __uint_as_float(r[j]), -tk[ch * 32 + j]); };
         float m4[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            m4[q] = g[8 * q];
+            m4[q] = gval(8 * q);
 #pragma unroll
-            for (int j = 1; j < 8; ++j) m4[q] = fminf(m4[q], g[8 * q + j]);
+            for (int j = 1; j < 8; ++j) m4[q] = fminf(m4[q], gval(8 * q + j));
         }
         const float gmin = fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
         if (!__any_sync(FULL_MASK, gmin < nxk)) return;
@@ -118,7 +118,7 @@ __device__ __forceinline__ void column_tile(const FusedParams &FP, EmitQueue &Q,
         // that assign the column-buffer slots are in flight together.
         unsigned int m = 0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) m |= (g[j] < nxk) ? (1u << j) : 0u;
+        for (int j = 0; j < 32; ++j) m |= (gval(j) < nxk) ? (1u << j) : 0u;
         for (;;) {
             const bool have = m != 0;
             const unsigned int has = __ballot_sync(FULL_MASK, have);

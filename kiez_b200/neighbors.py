@@ -330,10 +330,10 @@ class B200Mixin:
         return self._prepare(data, cache=True, lazy=True)
 
     # Host inputs (what kiez passes): upload on a background thread in row chunks, overlapped
-    # with the searches (kiez_b200/upload.py).  Order: the target first -- the first launches of
-    # the reverse / dual-direction pass need all of it --, then the strided row sample of the
-    # source that seeds the column thresholds, then the source, whose row segments the pass
-    # consumes in order.  KB2_ASYNC_UPLOAD=0 restores the plain synchronous copies.
+    # with the searches (kiez_b200/upload.py).  Order: the strided row sample of the source that
+    # seeds the column thresholds (small), then the target -- the threshold search consumes it
+    # chunk by chunk as it arrives --, then the source, whose row segments the dual-direction
+    # pass consumes in order.  KB2_ASYNC_UPLOAD=0 restores the plain synchronous copies.
     ASYNC_UPLOAD_MIN_BYTES = 8 << 20
 
     def _start_uploads(self, source, target, only_fit_target):
@@ -380,13 +380,13 @@ class B200Mixin:
                 host[::stride].mean(axis=0, dtype=np.float64).astype(np.float32)).to(self.device)
         up = upload.Uploader()
         with torch.cuda.device(self.device):
+            if any(m is source for m in mats) and target is not None and not only_fit_target:
+                cap = candidate_capacity(self.n_candidates)
+                n_s = self._fused_sample_rows(source.shape[0], cap)
+                step = max(1, source.shape[0] // n_s)
+                self._pending_uploads[("sample", id(source))] = (
+                    (n_s, step), up.add(upload.HostUpload(source, self.device, rows=(n_s, step))))
             for m in mats:
-                if m is source and target is not None and not only_fit_target:
-                    cap = candidate_capacity(self.n_candidates)
-                    n_s = self._fused_sample_rows(m.shape[0], cap)
-                    step = max(1, m.shape[0] // n_s)
-                    self._pending_uploads[("sample", id(m))] = (
-                        (n_s, step), up.add(upload.HostUpload(m, self.device, rows=(n_s, step))))
                 self._pending_uploads[id(m)] = up.add(upload.HostUpload(m, self.device))
         up.start()
         self._uploader = up
@@ -751,6 +751,7 @@ class B200Mixin:
     FUSED_SEGMENT_GROWTH = float(os.environ.get("KB2_FUSED_GROWTH", "3"))     # <= 1: one segment
     FUSED_SEGMENT_MIN_ROWS = int(os.environ.get("KB2_FUSED_MIN_ROWS", "16384"))
     FUSED_COL_CAP = int(os.environ.get("KB2_FUSED_COL_CAP", "512"))          # slots per column buffer
+    SAMPLE_CHUNK_ROWS = 131072      # columns per threshold-search launch while the host upload runs
 
     def _use_fused(self, rows: PreparedRows, cols: PreparedRows, k: int) -> bool:
         if self.fused is False or self.impl in ("simt", "tc1"):
@@ -817,7 +818,6 @@ class B200Mixin:
             sm = torch.cuda.get_device_properties(dev).multi_processor_count
             screen = self._use_screen(rows, cols, cap, dual=True)
             prof = getattr(self, "_profile", None)       # bench.py: CUDA events around the searches
-            cols.ensure()
             # 1. column thresholds from a strided sample of the rows (a host matrix still being
             #    uploaded sent exactly these rows ahead, see _start_uploads); with sharded rows
             #    every rank searches its share of the sample
@@ -842,8 +842,25 @@ class B200Mixin:
                 tau = torch.empty((0,), dtype=torch.float32, device=dev)
                 s_key = _s_idx = None
             elif screen and self._use_screen(s_cols, sample, cap, dual=False):
-                _s_idx, s_key, lists = self._screen_search(s_cols, sample, cap)
+                if s_cols._pending is not None and s_cols.n >= 2 * self.SAMPLE_CHUNK_ROWS:
+                    # the columns are still arriving from the host: search them chunk by chunk
+                    # (each launch waits only for its own rows), the upload hides behind the search
+                    tau = torch.empty((s_cols.n,), dtype=torch.float32, device=dev)
+                    for c_lo in range(0, s_cols.n, self.SAMPLE_CHUNK_ROWS):
+                        c_hi = min(s_cols.n, c_lo + self.SAMPLE_CHUNK_ROWS)
+                        if s_cols.n - c_hi < self.SAMPLE_CHUNK_ROWS // 2:
+                            c_hi = s_cols.n
+                        _i, k_part, l_part = self._screen_search(s_cols.rows(c_lo, c_hi), sample, cap)
+                        tau[c_lo:c_hi] = k_part.view(c_hi - c_lo, l_part, cap)[:, :, cap - 1].amin(dim=1)
+                        del _i, k_part
+                        if c_hi == s_cols.n:
+                            break
+                    s_key = _s_idx = None
+                else:
+                    s_cols.ensure()
+                    _s_idx, s_key, lists = self._screen_search(s_cols, sample, cap)
             else:
+                s_cols.ensure()
                 lists = lib.lib.kb2_suggest_splits(s_cols.n, n_s, cap, sm)
                 _s_idx = torch.empty((s_cols.n, lists * cap), dtype=torch.int32, device=dev)
                 s_key = torch.empty((s_cols.n, lists * cap), dtype=torch.float32, device=dev)
@@ -863,6 +880,7 @@ class B200Mixin:
             if comm is not None:
                 tau = comm.gather_columns(tau, cols.n)
             del _s_idx, s_key, sample
+            cols.ensure()
             # 2. the dual-direction pass, one launch per row segment; exact finish of the row
             #    lists per segment; thresholds tighten between segments
             col_cap = self._fused_col_cap(cap)

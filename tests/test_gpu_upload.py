@@ -20,11 +20,13 @@ def _data(n, m, d, seed):
             rng.standard_normal((m, d)).astype(np.float32))
 
 
-def _fit_predict(source, target, hubness, fused, c=10, k=5):
+def _fit_predict(source, target, hubness, fused, c=10, k=5, sample_chunk=None):
     from kiez_b200 import B200, Kiez
 
     algo = B200(n_candidates=c, fused=fused)
     algo.FUSED_SEGMENT_MIN_ROWS = 4096
+    if sample_chunk:
+        algo.SAMPLE_CHUNK_ROWS = sample_chunk    # threshold search in chunks of the arriving target
     inst = Kiez(n_candidates=c, algorithm=algo, hubness=hubness)
     inst.fit(source, target)
     return inst, inst.kneighbors(k)
@@ -42,7 +44,8 @@ def test_overlapped_upload_matches_device_inputs(kind, fused):
         src, tgt = torch.from_numpy(source), torch.from_numpy(target)
     else:
         src, tgt = source, target
-    inst, (dist, ind) = _fit_predict(src, tgt, "CSLS", fused)
+    inst, (dist, ind) = _fit_predict(src, tgt, "CSLS", fused,
+                                     sample_chunk=16384 if kind == "pageable" else None)
     algo = inst.algorithm
     assert algo._uploader is not None and len(algo._uploader.jobs) == 3     # target, sample, source
     assert algo._prepared[id(src)]._pending is None                         # everything consumed
