@@ -23,10 +23,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU legs (cpu_baseline on rank 0,
-# --impl reference) must be allowed all host threads, so undo that before numpy/sklearn load.
-if os.environ.get("OMP_NUM_THREADS") == "1" and int(os.environ.get("RANK", "0")) == 0:
-    os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
+# torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU legs (--impl reference, and the
+# parity oracle on rank 0) must be allowed all host threads, and every rank of the GPU arm its
+# share of them (host-side copies of the upload), so undo that before numpy/sklearn/torch load.
+if os.environ.get("OMP_NUM_THREADS") == "1":
+    _cores = len(os.sched_getaffinity(0))
+    _reference = "--impl" in sys.argv and "reference" in sys.argv
+    _world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
+    if int(os.environ.get("RANK", "0")) == 0:
+        os.environ["OMP_NUM_THREADS"] = str(_cores if _reference else max(1, _cores // 2))
+    else:
+        os.environ["OMP_NUM_THREADS"] = str(max(1, _cores // (2 * _world)))
 
 import numpy as np
 

@@ -86,9 +86,7 @@ __device__ __forceinline__ void load_taucol(const float *__restrict__ tau_col, i
 // One accumulator tile (this warp's 32 TMEM lanes x BN columns), column side.
 // `tk` = this warp's shared copy of the tile's thresholds, xk = x_key of this thread's row
 // (+inf for rows that do not exist: they never emit), row_base = row of lane 0.
-// DOUBLE_BUFFER: the next chunk's tcgen05.ld is in flight while this one is tested (needs the
-// register budget of setmaxnreg, see knn_screen.cu).
-template <int BN, bool DOUBLE_BUFFER = false>
+template <int BN>
 __device__ __forceinline__ void column_tile(const FusedParams &FP, EmitQueue &Q, const float *tk,
                                             uint32_t taddr, int64_t c0, float xk, int64_t row_base,
                                             int lane) {
@@ -145,26 +143,15 @@ __device__ __forceinline__ void column_tile(const FusedParams &FP, EmitQueue &Q,
             if (Q.n > EMIT_Q - 32) emit_flush(FP, Q, row_base, lane);
         }
     };
+    // (Keeping the next chunk's tcgen05.ld in flight while this one is tested -- with and without
+    // a larger register budget -- measured no faster, profiles/r02_ab_experiments.md block M: two
+    // epilogue warps per scheduler already hide the TMEM latency.)
     uint32_t ra[32];
-    if constexpr (!DOUBLE_BUFFER) {
 #pragma unroll 1
-        for (int ch = 0; ch < NCH; ++ch) {
-            tmem_ld_32x32b_x32(taddr + ch * 32, ra);
-            tmem_ld_wait();
-            process(ra, ch);
-        }
-        return;
-    }
-    uint32_t rb[32];
-    tmem_ld_32x32b_x32(taddr, ra);
-#pragma unroll 1
-    for (int ch = 0; ch < NCH; ch += 2) {
+    for (int ch = 0; ch < NCH; ++ch) {
+        tmem_ld_32x32b_x32(taddr + ch * 32, ra);
         tmem_ld_wait();
-        tmem_ld_32x32b_x32(taddr + (ch + 1) * 32, rb);   // in flight while ra is tested
         process(ra, ch);
-        tmem_ld_wait();
-        if (ch + 2 < NCH) tmem_ld_32x32b_x32(taddr + (ch + 2) * 32, ra);
-        process(rb, ch + 1);
     }
 }
 

@@ -70,13 +70,8 @@ __device__ __forceinline__ void st_release(int *p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// DB (dual-direction form, A/B behind KB2_DUAL_DB=1): the COLUMN epilogue warps keep the next
-// chunk's tcgen05.ld in flight while they test the current one, as the one-direction row
-// epilogue always does (the column test no longer stores its 32 keys, so this fits the 168
-// registers of the dual form without spills; double-buffering the row side as well spills),
-// and the block drops its two idle warps (10 warps).
-template <bool DUAL, bool DB = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DUAL ? (DB ? 320 : 384) : 192, 1)
+template <bool DUAL>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DUAL ? 384 : 192, 1)
 knn_screen_kernel(const __grid_constant__ CUtensorMap map_q,
                   const __grid_constant__ CUtensorMap map_y, const ScreenParams P,
                   const FusedParams FP) {
@@ -372,7 +367,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap map_q,
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-                column_tile<BN, DB>(FP, Q, tk, taddr, c0, xk, row_base, lane);
+                column_tile<BN>(FP, Q, tk, taddr, c0, xk, row_base, lane);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(tmem_empty_leader + (uint32_t)acc * 8);
@@ -437,7 +432,7 @@ static int screen_config(int dpad, int cap, bool dual, int max_smem, int *slots_
     return stages >= 3 ? stages : 0;
 }
 
-template <bool DUAL, bool DB = false>
+template <bool DUAL>
 static int launch_screen(ScreenParams P, const FusedParams &FP, const float *q_hi, const float *y_hi,
                          int dpad, int sm_count, int max_smem, cudaStream_t stream) {
     CUtensorMap mq, my;
@@ -446,13 +441,13 @@ static int launch_screen(ScreenParams P, const FusedParams &FP, const float *q_h
     const size_t need = (size_t)(P.resident + P.stages) * S_HALF * S_BK * 4 +
                         screen_fixed_smem(P.cap, P.buf_slots, DUAL);
     const size_t smem = min((size_t)max_smem, need + 1024);
-    KB2_CUDA(cudaFuncSetAttribute(knn_screen_kernel<DUAL, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    KB2_CUDA(cudaFuncSetAttribute(knn_screen_kernel<DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     const int64_t units = ((P.q_tiles + 1) / 2) * P.steps;
     const unsigned pairs = (unsigned)min((int64_t)(sm_count / 2), units);
     if (P.chained)
         KB2_CUDA(cudaMemsetAsync(P.chain_flag, 0, (size_t)P.q_tiles * 4 * sizeof(int), stream));
-    knn_screen_kernel<DUAL, DB><<<2 * pairs, DUAL ? (DB ? 320 : 384) : 192, smem, stream>>>(mq, my, P, FP);
+    knn_screen_kernel<DUAL><<<2 * pairs, DUAL ? 384 : 192, smem, stream>>>(mq, my, P, FP);
     KB2_LAUNCH_CHECK();
     return 0;
 }
@@ -543,11 +538,6 @@ extern "C" int kb2_knn_screen(const float *q_hi, const float *q_key, int64_t nq,
     FP.col_buf = reinterpret_cast<ent_t *>(col_buf); FP.col_cap = col_cap;
     FP.row_id_base = (int)row_id_base;
     cudaStream_t st = (cudaStream_t)stream;
-    if (dual) {
-        const char *db = getenv("KB2_DUAL_DB");           // A/B: double-buffered TMEM loads, 10 warps
-        if (db && db[0] == '1')
-            return launch_screen<true, true>(P, FP, q_hi, y_hi, dpad, sm_count, max_smem, st);
-        return launch_screen<true>(P, FP, q_hi, y_hi, dpad, sm_count, max_smem, st);
-    }
+    if (dual) return launch_screen<true>(P, FP, q_hi, y_hi, dpad, sm_count, max_smem, st);
     return launch_screen<false>(P, FP, q_hi, y_hi, dpad, sm_count, max_smem, st);
 }

@@ -508,13 +508,35 @@ __device__ __forceinline__ unsigned long long sortable_bits(double v) {
     return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
 }
 
+// Block = 128 consecutive rows.  Global memory is only touched with coalesced accesses: the
+// block's contiguous span of the (n, c) arrays is copied into shared memory (row stride padded
+// to an odd number of 8-byte words: conflict-free per-row reads), every thread takes its row
+// into registers, and the results go back through the same buffers.
+constexpr int SMALL_ROWS = 128;
+__host__ __device__ inline int small_stride(int width) { return width | 1; }
+
 template <int C>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(SMALL_ROWS)
 rows_small_kernel(const RgParams p) {
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= p.n) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int total = p.c * p.nparts;
+    const int ld = small_stride(total);
+    double *sd = reinterpret_cast<double *>(smem_raw);                       // [SMALL_ROWS][ld]
+    int64_t *si = reinterpret_cast<int64_t *>(sd + (size_t)SMALL_ROWS * ld); // [SMALL_ROWS][ld]
+    const int64_t row0 = (int64_t)blockIdx.x * SMALL_ROWS;
+    const int rows_here = (int)min((int64_t)SMALL_ROWS, p.n - row0);
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int part = 0; part < p.nparts; ++part) {
+        const double *gd = p.dist + (int64_t)part * p.part_stride + row0 * p.c;
+        const int64_t *gi = p.ind + (int64_t)part * p.part_stride + row0 * p.c;
+        for (int e = threadIdx.x; e < rows_here * p.c; e += SMALL_ROWS) {
+            const int r = e / p.c, j = e - r * p.c;
+            sd[r * ld + part * p.c + j] = gd[e];
+            si[r * ld + part * p.c + j] = gi[e];
+        }
+    }
+    __syncthreads();
+    const bool row_ok = threadIdx.x < rows_here;
     double x[C];
     int64_t id[C];
     double s = 0.0, sn = 0.0, cnt = 0.0;
@@ -522,11 +544,9 @@ rows_small_kernel(const RgParams p) {
     for (int e = 0; e < C; ++e) {
         x[e] = qnan;
         id[e] = -1;
-        if (e < total) {
-            const int part = e / p.c;
-            const int64_t off = (int64_t)part * p.part_stride + row * p.c + (e - part * p.c);
-            x[e] = p.dist[off];
-            id[e] = p.ind[off];
+        if (row_ok && e < total) {
+            x[e] = sd[threadIdx.x * ld + e];
+            id[e] = si[threadIdx.x * ld + e];
             s += x[e];
             if (!isnan(x[e])) { sn += x[e]; cnt += 1.0; }
         }
@@ -534,15 +554,15 @@ rows_small_kernel(const RgParams p) {
     double r[C];
     if (p.op <= KB2_RESCALE_MP_GAUSS) {
         const double mean = s / (double)p.c;                              // ndarray.mean
-        double mu = 0.0, sd = 0.0, last = 0.0;
-        if (p.op == KB2_RESCALE_LS) last = p.dist[row * p.c + p.c - 1];    // (same cache line)
+        double mu = 0.0, sd_row = 0.0, last = 0.0;
+        if (p.op == KB2_RESCALE_LS && row_ok) last = sd[threadIdx.x * ld + p.c - 1];
         if (p.op == KB2_RESCALE_MP_GAUSS) {                               // nanmean / nanstd(ddof=0)
             mu = sn / cnt;
             double q = 0.0;
 #pragma unroll
             for (int e = 0; e < C; ++e)
                 if (!isnan(x[e])) { const double d = x[e] - mu; q += d * d; }
-            sd = sqrt(q / cnt);
+            sd_row = sqrt(q / cnt);
         }
 #pragma unroll
         for (int e = 0; e < C; ++e) {
@@ -556,7 +576,7 @@ rows_small_kernel(const RgParams p) {
                 r[e] = x[e] / sqrt(mean * a);
             } else {
                 const double sb = ok ? __ldg(p.stat_b + id[e]) : qnan;
-                r[e] = 1.0 - norm_sf(x[e], mu, sd) * norm_sf(x[e], a, sb);
+                r[e] = 1.0 - norm_sf(x[e], mu, sd_row) * norm_sf(x[e], a, sb);
             }
         }
     } else if (p.op == RG_OP_DSL_FINISH) {
@@ -571,53 +591,74 @@ rows_small_kernel(const RgParams p) {
 #pragma unroll
         for (int e = 0; e < C; ++e) r[e] = x[e];
     }
+    __syncthreads();                                     // every row is in registers: reuse the buffers
+    const int width = p.k == 0 ? total : p.k;            // values written per row
     if (p.k == 0) {                                      // HubnessReduction.transform: unsorted
 #pragma unroll
         for (int e = 0; e < C; ++e) {
-            if (e < total) {
-                p.out_dist[row * total + e] = r[e];
-                p.out_ind[row * total + e] = id[e];
+            if (row_ok && e < total) {
+                sd[threadIdx.x * ld + e] = r[e];
+                si[threadIdx.x * ld + e] = id[e];
             }
         }
-        return;
+    } else {
+        unsigned long long u[C];
+#pragma unroll
+        for (int e = 0; e < C; ++e) u[e] = (e < total) ? sortable_bits(r[e]) : ~0ull;
+#pragma unroll
+        for (int e = 0; e < C; ++e) {
+            if (e >= total) continue;
+            int rank = 0;                                // entries ordered before e: (value, position)
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                if (j == e) continue;
+                rank += (j < e) ? (u[j] <= u[e]) : (u[j] < u[e]);
+            }
+            if (row_ok && rank < p.k) {
+                sd[threadIdx.x * ld + rank] = r[e];
+                si[threadIdx.x * ld + rank] = id[e];
+            }
+        }
     }
-    unsigned long long u[C];
-#pragma unroll
-    for (int e = 0; e < C; ++e) u[e] = (e < total) ? sortable_bits(r[e]) : ~0ull;
-#pragma unroll
-    for (int e = 0; e < C; ++e) {
-        if (e >= total) continue;
-        int rank = 0;                                    // entries ordered before e: (value, position)
-#pragma unroll
-        for (int j = 0; j < C; ++j) {
-            if (j == e) continue;
-            rank += (j < e) ? (u[j] <= u[e]) : (u[j] < u[e]);
-        }
-        if (rank < p.k) {
-            p.out_dist[row * p.k + rank] = r[e];
-            p.out_ind[row * p.k + rank] = id[e];
-        }
+    __syncthreads();
+    double *od = p.out_dist + row0 * width;
+    int64_t *oi = p.out_ind + row0 * width;
+    for (int e = threadIdx.x; e < rows_here * width; e += SMALL_ROWS) {
+        const int rr = e / width, j = e - rr * width;
+        od[e] = sd[rr * ld + j];
+        oi[e] = si[rr * ld + j];
     }
 }
 
 template <int C>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(SMALL_ROWS)
 row_stats_small_kernel(const double *__restrict__ dist, int64_t n, int c, double *__restrict__ mean,
                        double *__restrict__ sd, double *__restrict__ last) {
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= n) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int ld = small_stride(c);
+    double *sx = reinterpret_cast<double *>(smem_raw);                       // [SMALL_ROWS][ld]
+    const int64_t row0 = (int64_t)blockIdx.x * SMALL_ROWS;
+    const int rows_here = (int)min((int64_t)SMALL_ROWS, n - row0);
+    const double *gd = dist + row0 * c;
+    for (int e = threadIdx.x; e < rows_here * c; e += SMALL_ROWS) {
+        const int r = e / c;
+        sx[r * ld + (e - r * c)] = gd[e];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x >= rows_here) return;
+    const int64_t row = row0 + threadIdx.x;
     double x[C];
     double s = 0.0, sn = 0.0, cnt = 0.0;
 #pragma unroll
     for (int e = 0; e < C; ++e) {
         x[e] = __longlong_as_double(0x7ff8000000000000LL);
         if (e < c) {
-            x[e] = dist[row * c + e];
+            x[e] = sx[threadIdx.x * ld + e];
             s += x[e];
             if (!isnan(x[e])) { sn += x[e]; cnt += 1.0; }
         }
     }
-    const double lst = dist[row * c + c - 1];              // (same cache line)
+    const double lst = sx[threadIdx.x * ld + c - 1];
     const double mu = sn / cnt;
     double q = 0.0;
 #pragma unroll
@@ -632,10 +673,11 @@ row_stats_small_kernel(const double *__restrict__ dist, int64_t n, int c, double
 constexpr int SMALL_MAX_WIDTH = 16;
 static int launch_rows_small(const RgParams &p, cudaStream_t st) {
     const int total = p.c * p.nparts;
-    const unsigned grid = (unsigned)ceil_div64(p.n, 128);
-    if (total <= 8) rows_small_kernel<8><<<grid, 128, 0, st>>>(p);
-    else if (total <= 12) rows_small_kernel<12><<<grid, 128, 0, st>>>(p);
-    else rows_small_kernel<16><<<grid, 128, 0, st>>>(p);
+    const unsigned grid = (unsigned)ceil_div64(p.n, SMALL_ROWS);
+    const size_t smem = (size_t)SMALL_ROWS * small_stride(total) * 16;
+    if (total <= 8) rows_small_kernel<8><<<grid, SMALL_ROWS, smem, st>>>(p);
+    else if (total <= 12) rows_small_kernel<12><<<grid, SMALL_ROWS, smem, st>>>(p);
+    else rows_small_kernel<16><<<grid, SMALL_ROWS, smem, st>>>(p);
     KB2_LAUNCH_CHECK();
     return 0;
 }
@@ -665,10 +707,11 @@ struct StatsLauncher {
     static int run(const double *dist, int64_t n, int c, double *mean, double *sd, double *last,
                    cudaStream_t st) {
         if (c <= SMALL_MAX_WIDTH) {
-            const unsigned grid = (unsigned)ceil_div64(n, 128);
-            if (c <= 8) row_stats_small_kernel<8><<<grid, 128, 0, st>>>(dist, n, c, mean, sd, last);
-            else if (c <= 12) row_stats_small_kernel<12><<<grid, 128, 0, st>>>(dist, n, c, mean, sd, last);
-            else row_stats_small_kernel<16><<<grid, 128, 0, st>>>(dist, n, c, mean, sd, last);
+            const unsigned grid = (unsigned)ceil_div64(n, SMALL_ROWS);
+            const size_t smem = (size_t)SMALL_ROWS * small_stride(c) * 8;
+            if (c <= 8) row_stats_small_kernel<8><<<grid, SMALL_ROWS, smem, st>>>(dist, n, c, mean, sd, last);
+            else if (c <= 12) row_stats_small_kernel<12><<<grid, SMALL_ROWS, smem, st>>>(dist, n, c, mean, sd, last);
+            else row_stats_small_kernel<16><<<grid, SMALL_ROWS, smem, st>>>(dist, n, c, mean, sd, last);
             KB2_LAUNCH_CHECK();
             return 0;
         }

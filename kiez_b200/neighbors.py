@@ -752,6 +752,7 @@ class B200Mixin:
     FUSED_SEGMENT_MIN_ROWS = int(os.environ.get("KB2_FUSED_MIN_ROWS", "16384"))
     FUSED_COL_CAP = int(os.environ.get("KB2_FUSED_COL_CAP", "512"))          # slots per column buffer
     SAMPLE_CHUNK_ROWS = 131072      # columns per threshold-search launch while the host upload runs
+    FUSED_RANK_MIN_ROWS = 38144     # rows per rank and segment of a row-sharded pass (298 query tiles)
 
     def _use_fused(self, rows: PreparedRows, cols: PreparedRows, k: int) -> bool:
         if self.fused is False or self.impl in ("simt", "tc1"):
@@ -782,14 +783,14 @@ class B200Mixin:
     def _fused_sample_rows(self, n_rows: int, cap: int) -> int:
         return int(min(n_rows, max(8 * cap, -(-n_rows // max(1.0, self.FUSED_SAMPLE_DIV)))))
 
-    def _fused_segments(self, n_rows: int, n_sample: int):
+    def _fused_segments(self, n_rows: int, n_sample: int, min_rows: int = 0):
         """Row segment boundaries [0, b1, ..., n_rows] (multiples of 256 = one tile pair)."""
         g = self.FUSED_SEGMENT_GROWTH
         if g <= 1.0:
             return [0, n_rows]
         bounds, seen = [0], max(1, n_sample)
         while bounds[-1] < n_rows:
-            size = max(int((g - 1.0) * seen), self.FUSED_SEGMENT_MIN_ROWS, 256)
+            size = max(int((g - 1.0) * seen), self.FUSED_SEGMENT_MIN_ROWS, min_rows, 256)
             nxt = (bounds[-1] + size + 255) // 256 * 256
             if n_rows - nxt < size // 2:        # fold a short tail into this segment
                 nxt = n_rows
@@ -889,7 +890,12 @@ class B200Mixin:
             fwd_d = torch.empty((rows.n, k_rows), dtype=torch.float64, device=dev)
             fwd_i = torch.empty((rows.n, k_rows), dtype=torch.int64, device=dev)
             unv_rows = torch.zeros((rows.n,), dtype=torch.int32, device=dev) if screen else None
-            bounds = self._fused_segments(n_total, n_s_total)
+            # sharded rows: every rank's share of a segment should still fill the GPU with chained
+            # query tiles (>= 2 tiles per SM), else the launch falls back to independent index
+            # ranges, whose lists each pay the fill phase again
+            bounds = self._fused_segments(
+                n_total, n_s_total,
+                min_rows=0 if comm is None else min(world * self.FUSED_RANK_MIN_ROWS, n_total // 2))
             if comm is not None:
                 # the same number of segments on every rank (the exchanges between them are
                 # collective), each a proportional share of the global segment

@@ -15,7 +15,9 @@ torch is used for what it is here for: device memory, streams, events.
 """
 from __future__ import annotations
 
+import os
 import threading
+from concurrent.futures import ThreadPoolExecutor
 from typing import List, Optional, Tuple
 
 import numpy as np
@@ -23,6 +25,10 @@ import torch
 
 CHUNK_BYTES = 32 << 20          # one staging buffer / one async copy
 RING = 3                        # staging buffers in flight
+# the pageable -> pinned memcpy of a chunk is split over this many helper threads (numpy / torch
+# copies release the GIL): torchrun exports OMP_NUM_THREADS=1 to every rank, which would leave a
+# single-threaded memcpy (~6 GB/s) as the bottleneck of the upload
+COPY_THREADS = max(1, min(4, (os.cpu_count() or 4) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
 
 _staging = {}                   # (device index, nbytes) -> ([pinned uint8 tensors], [last copy event])
 _copy_streams = {}              # device index -> torch.cuda.Stream
@@ -43,6 +49,16 @@ def _staging_ring(device, nbytes: int):
         _staging[key] = ([torch.empty(nbytes, dtype=torch.uint8, pin_memory=True) for _ in range(RING)],
                          [None] * RING)
     return _staging[key]
+
+
+_pool = None
+
+
+def _copy_pool():
+    global _pool
+    if _pool is None:
+        _pool = ThreadPoolExecutor(max_workers=COPY_THREADS, thread_name_prefix="kiez_b200-memcpy")
+    return _pool
 
 
 def eligible(data) -> bool:
@@ -99,6 +115,7 @@ class HostUpload:
             pinned = self._gather is None and self.host.is_pinned()
             ring, ring_events = (None, None) if pinned else \
                 _staging_ring(self.device, self.chunk_rows * self.d * 4)
+            pool = _copy_pool() if not pinned and COPY_THREADS > 1 else None
             for i, (lo, hi) in enumerate(self.bounds):
                 if pinned:
                     src = self.host[lo:hi]
@@ -108,10 +125,16 @@ class HostUpload:
                         ring_events[slot].synchronize()      # the copy that used this buffer is done
                     buf = ring[slot][: (hi - lo) * self.d * 4].view(torch.float32).view(hi - lo, self.d)
                     if self._gather is None:
-                        buf.copy_(self.host[lo:hi])
+                        part = self.host[lo:hi]
                     else:
                         step = self._gather[1]
-                        buf.copy_(self.host[lo * step: (hi - 1) * step + 1: step])
+                        part = self.host[lo * step: (hi - 1) * step + 1: step]
+                    if pool is None or hi - lo < 4 * COPY_THREADS:
+                        buf.copy_(part)
+                    else:
+                        cuts = [(hi - lo) * t // COPY_THREADS for t in range(COPY_THREADS + 1)]
+                        list(pool.map(lambda ab: buf[ab[0]:ab[1]].copy_(part[ab[0]:ab[1]]),
+                                      zip(cuts[:-1], cuts[1:])))
                     src = buf
                 with torch.cuda.stream(stream):
                     self.dev[lo:hi].copy_(src, non_blocking=True)
