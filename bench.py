@@ -315,12 +315,13 @@ def measured_peaks():
 def ncu_traffic(kind):
     """DRAM bytes (read + write) of ONE launch of the dominant kernel from the committed
     `ncu --set full` summary under profiles/ (tools/ncu_summary.py), or None."""
-    name = {"screen-dual": "r01_ncu_knn_screen_dual_final.txt",
-            "screen": "r01_ncu_knn_screen_rows.txt",
-            "tf32x3-dual": "r01_ncu_knn_fused.txt",
-            "tf32x3": "r01_ncu_knn_tc2_pair_bk32.txt"}.get(kind)
+    names = {"screen-dual": ("r02_ncu_knn_screen_dual.txt", "r01_ncu_knn_screen_dual_final.txt"),
+             "screen": ("r02_ncu_knn_screen_c50.txt", "r01_ncu_knn_screen_rows.txt"),
+             "tf32x3-dual": ("r01_ncu_knn_fused.txt",),
+             "tf32x3": ("r01_ncu_knn_tc2_pair_bk32.txt",)}.get(kind, ())
+    name = next((nm for nm in names if os.path.exists(os.path.join(ROOT, "profiles", nm))), None)
     path = os.path.join(ROOT, "profiles", name) if name else None
-    if not path or not os.path.exists(path):
+    if not path:
         return None, None
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
     total, ms = 0.0, None

@@ -56,6 +56,19 @@ def main():
         O.assert_neighbors_match(_np(dist)[rows], _np(idx)[rows], wd, wi, 1e-5, 5e-6, what="chained")
         del os.environ["KB2_SCREEN_RANGE_MB"]
         print("ok screen chained ranges", flush=True)
+        # long lists at d = 256: 5 of 8 K chunks of the query tile resident, the rest streamed
+        q = rng.standard_normal((600, 256)).astype(np.float32)
+        y = rng.standard_normal((3000, 256)).astype(np.float32)
+        for fused in (False, True):
+            algo = B200(n_candidates=50, precision="screen", fused=fused)
+            qp, yp = algo._prepare(q, cache=False), algo._prepare(y, cache=False)
+            if fused:
+                (dist, idx), _rev = algo.search_both(qp, yp, 50, 50)
+            else:
+                dist, idx = algo.search(qp, yp, 50)
+            wd, wi = O.knn_brute(q.astype(np.float64), y.astype(np.float64), 50, "euclidean")
+            O.assert_neighbors_match(_np(dist), _np(idx), wd, wi, 1e-5, 5e-6, what="partial residency")
+        print("ok screen partially resident query tile", flush=True)
     if "tf32x3" in families:
         ind = run("3xTF32 pair dual", "csls", "CSLS", {}, impl="tc", precision="tf32x3", fused=True)
         run("3xTF32 pair", "nicdm", "LocalScaling", {"method": "nicdm"}, impl="tc",
