@@ -164,10 +164,13 @@ int kb2_kth_key(const float *keys, int nparts, int64_t part_stride, int64_t ny, 
  *   supported (dpad > 1024, cap > 128).  kb2_screen_config additionally reports the append-buffer
  *   slots per list and how many of the dpad/32 K chunks of the query tile stay resident in
  *   shared memory (the rest is streamed through the ring with the index tiles); max_smem <= 0 =
- *   the current device's opt-in limit (pass 232448 to evaluate the B200 plan without a device).
+ *   the current device's opt-in limit (pass 232448 to evaluate the B200 plan without a device);
+ *   ny = index rows one list sweeps (0 = long index): short indexes with long lists get longer
+ *   append buffers (fewer list merges) at the price of resident query chunks.
  */
 int kb2_screen_stages(int dpad, int cap, int dual);
-int kb2_screen_config(int dpad, int cap, int dual, int max_smem, int *slots, int *resident);
+int kb2_screen_config(int dpad, int cap, int dual, int max_smem, int64_t ny, int *slots,
+                      int *resident);
 int kb2_screen_plan(int64_t nq, int64_t ny, int dpad, int cap, int sm_count, int *steps,
                     int *chained);
 int kb2_knn_screen(const float *q_hi, const float *q_key, int64_t nq, const float *y_hi,

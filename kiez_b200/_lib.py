@@ -40,7 +40,7 @@ SIGNATURES = {
     "kb2_col_heads": [_p, _p, _i64, _int, _int, _i64, _p, _p, _p],
     "kb2_kth_key": [_p, _int, _i64, _i64, _int, _int, _p, _p],
     "kb2_screen_stages": [_int, _int, _int],
-    "kb2_screen_config": [_int, _int, _int, _int, _p, _p],
+    "kb2_screen_config": [_int, _int, _int, _int, _i64, _p, _p],
     "kb2_screen_plan": [_i64, _i64, _int, _int, _int, _p, _p],
     "kb2_knn_screen": [_p, _p, _i64, _p, _p, _i64, _int, _int, _int, _int, _p, _p, _p, _p, _p, _p,
                        _int, _i64, _p],

@@ -400,9 +400,17 @@ static size_t screen_fixed_smem(int cap, int slots, bool dual) {
 // size and how many K chunks of the query tile stay resident.  Shared memory left by the lists
 // is cut into 16 KB units; at least SCREEN_MIN_STAGES of them form the ring, the rest hold
 // query chunks.  A fully resident tile gets the remaining units as extra ring slots.
+//
+// `ny` (index rows one list sweeps; 0 = long index): a row accepts ~cap ln(ny / cap) entries
+// whatever the key precision, and every `slots - 4` of them cost one warp-wide list merge.  Over
+// a long index (C4: 1 M rows) that is noise next to the 4096 tensor cycles of an index tile and
+// the shared memory is better spent on residency; over a short one with long lists (C3: cap 112,
+// 100 k rows; C2: cap 56, 15 k rows) the merges ARE the kernel (C3 ran 39 k cycles per tile with
+// 12-slot buffers), so the append buffers grow -- at the price of resident query chunks -- until
+// the estimated merge work per tile drops below a quarter of the tile's tensor time.
 constexpr int SCREEN_MIN_STAGES = 4;
 static int screen_config(int dpad, int cap, bool dual, int max_smem, int *slots_out,
-                         int *resident_out = nullptr) {
+                         int *resident_out = nullptr, int64_t ny = 0) {
     if (dpad <= 0 || dpad % S_BK != 0 || dpad > S_MAX_DPAD || cap <= 0 || cap > 128) return 0;
     const int kchunks = dpad / S_BK;
     const size_t unit = (size_t)S_HALF * S_BK * 4;
@@ -418,6 +426,19 @@ static int screen_config(int dpad, int cap, bool dual, int max_smem, int *slots_
         if (min(kchunks + SCREEN_MIN_STAGES, units_for(cand)) >
             min(kchunks + SCREEN_MIN_STAGES, units_for(slots)))
             slots = cand;
+    if (ny > 0) {
+        const int regs = cap <= 16 ? 1 : cap <= 32 ? 2 : cap <= 64 ? 4 : 8;      // list_merge<R>
+        const int max_slots = cap <= 16 ? 16 : cap <= 32 ? 32 : 64;
+        const double appends = cap * log(fmax(2.0, (double)ny / cap));            // per row
+        const double merge_instr = 150.0 + 90.0 * regs;                           // warp-wide, per merge
+        const double tiles = fmax(1.0, (double)ny / S_BN);
+        auto merge_load = [&](int sl) {      // warp instructions per index tile spent merging
+            return 32.0 * appends / (sl - LISTS_GROUP) * merge_instr / tiles;
+        };
+        while (merge_load(slots) > 1024.0 && slots + LISTS_GROUP <= max_slots &&
+               units_for(slots + LISTS_GROUP) >= SCREEN_MIN_STAGES)
+            slots += LISTS_GROUP;
+    }
     const int units = units_for(slots);
     int resident = min(kchunks, units - SCREEN_MIN_STAGES);
     if (resident < 0) resident = 0;
@@ -464,7 +485,7 @@ extern "C" int kb2_screen_stages(int dpad, int cap, int dual) {
     return screen_config(dpad, cap, dual != 0, max_smem, nullptr);
 }
 
-extern "C" int kb2_screen_config(int dpad, int cap, int dual, int max_smem, int *slots,
+extern "C" int kb2_screen_config(int dpad, int cap, int dual, int max_smem, int64_t ny, int *slots,
                                  int *resident) {
     if (max_smem <= 0) {
         int dev = 0;
@@ -472,7 +493,7 @@ extern "C" int kb2_screen_config(int dpad, int cap, int dual, int max_smem, int 
         if (cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
             return 0;
     }
-    return screen_config(dpad, cap, dual != 0, max_smem, slots, resident);
+    return screen_config(dpad, cap, dual != 0, max_smem, slots, resident, ny);
 }
 
 extern "C" int kb2_screen_plan(int64_t nq, int64_t ny, int dpad, int cap, int sm_count,
@@ -526,7 +547,9 @@ extern "C" int kb2_knn_screen(const float *q_hi, const float *q_key, int64_t nq,
     P.per_step = ceil_div64(ceil_div64(ny, steps), S_BN) * S_BN;
     P.q_tiles = ceil_div64(nq, BM); P.y_key = y_key; P.cand_idx = cand_idx; P.cand_key = cand_key;
     P.chain_flag = chain_flag;
-    P.stages = screen_config(dpad, cap, dual, max_smem, &P.buf_slots, &P.resident);
+    // rows one candidate list sweeps: the whole index when the ranges are chained, else one range
+    P.stages = screen_config(dpad, cap, dual, max_smem, &P.buf_slots, &P.resident,
+                             chained ? ny : P.per_step);
     KB2_CHECK(P.stages > 0, "knn_screen: dpad=%d cap=%d is not supported (dpad <= %d, multiple of "
               "%d, cap <= 128; see kb2_screen_stages)", dpad, cap, S_MAX_DPAD, S_BK);
     if (const char *env = getenv("KB2_SCREEN_STAGES")) {

@@ -529,6 +529,8 @@ rows_small_kernel(const RgParams p) {
     for (int part = 0; part < p.nparts; ++part) {
         const double *gd = p.dist + (int64_t)part * p.part_stride + row0 * p.c;
         const int64_t *gi = p.ind + (int64_t)part * p.part_stride + row0 * p.c;
+        // (unrolled: the loads of four iterations are in flight before the first store)
+#pragma unroll 4
         for (int e = threadIdx.x; e < rows_here * p.c; e += SMALL_ROWS) {
             const int r = e / p.c, j = e - r * p.c;
             sd[r * ld + part * p.c + j] = gd[e];
@@ -623,6 +625,7 @@ rows_small_kernel(const RgParams p) {
     __syncthreads();
     double *od = p.out_dist + row0 * width;
     int64_t *oi = p.out_ind + row0 * width;
+#pragma unroll 4
     for (int e = threadIdx.x; e < rows_here * width; e += SMALL_ROWS) {
         const int rr = e / width, j = e - rr * width;
         od[e] = sd[rr * ld + j];
@@ -640,6 +643,7 @@ row_stats_small_kernel(const double *__restrict__ dist, int64_t n, int c, double
     const int64_t row0 = (int64_t)blockIdx.x * SMALL_ROWS;
     const int rows_here = (int)min((int64_t)SMALL_ROWS, n - row0);
     const double *gd = dist + row0 * c;
+#pragma unroll 4
     for (int e = threadIdx.x; e < rows_here * c; e += SMALL_ROWS) {
         const int r = e / c;
         sx[r * ld + (e - r * c)] = gd[e];

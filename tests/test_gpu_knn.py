@@ -328,9 +328,9 @@ def test_screen_partial_residency_plan():
 
     from kiez_b200 import _lib
 
-    def plan(dpad, cap, dual):
+    def plan(dpad, cap, dual, ny=0):
         slots, res = C.c_int(0), C.c_int(0)
-        stages = _lib.lib.kb2_screen_config(dpad, cap, dual, 0, C.addressof(slots), C.addressof(res))
+        stages = _lib.lib.kb2_screen_config(dpad, cap, dual, 0, ny, C.addressof(slots), C.addressof(res))
         return stages, slots.value, res.value
 
     assert plan(256, 16, 1)[2] == 8 and plan(256, 16, 1)[0] >= 4       # C4: fully resident
@@ -340,6 +340,10 @@ def test_screen_partial_residency_plan():
     assert st >= 4 and 1 <= res < 8
     assert plan(128, 56, 0)[2] == 4                                     # C5: fully resident
     assert plan(2048, 16, 0)[0] == 0 and plan(256, 136, 0)[0] == 0
+    # short indexes with long lists: longer append buffers (fewer merges), less residency
+    assert plan(256, 112, 0, 100_000)[1] > plan(256, 112, 0)[1] and plan(256, 112, 0, 100_000)[0] >= 4
+    assert plan(256, 56, 0, 15_000)[1] > plan(256, 56, 0)[1]
+    assert plan(256, 16, 1, 1_000_000) == plan(256, 16, 1)                # C4 is unaffected
 
 
 @pytest.mark.parametrize("fused", [False, True])
