@@ -25,7 +25,7 @@ def test_bench_traffic_lookup_reads_the_ncu_summary():
     spec.loader.exec_module(bench)
     traffic, source = bench.ncu_traffic("screen-dual")
     assert traffic is not None and 1e10 < traffic < 1e11
-    assert "r01_ncu_knn_screen_dual_final.txt" in source
+    assert "ncu_knn_screen_dual" in source and source.startswith("profiles/")
     assert bench.ncu_traffic("no-such-kind") == (None, None)
     # the CPU-leg sample stays bounded (about 10-30 s of work at C4)
     w = dict(bench.WORKLOADS["c4"])
