@@ -616,6 +616,13 @@ def run_b200(args, w):
         src_h, tgt_h = source.cpu(), target.cpu()
         t_page, d_, i_ = e2e_run(src_h.numpy(), tgt_h.numpy(), n_e2e)
         d2h = int(d_.nbytes + i_.nbytes) if isinstance(d_, np.ndarray) else 0
+        # when the last chunk of each upload job of the last step was handed to the copy engine,
+        # in ms after fit() began (jobs in order: row sample, target, source; N > 1: the slices)
+        up_ms = None
+        algo_e = last["inst"].algorithm
+        if getattr(algo_e, "_uploader", None) is not None:
+            up_ms = [round(1e3 * (j.t_enqueued[-1] - algo_e._t_fit_start), 1)
+                     for j in algo_e._uploader.jobs]
         src_p, tgt_p = src_h.pin_memory(), tgt_h.pin_memory()
         del src_h, tgt_h
         t_pin, _d, _i = e2e_run(src_p.numpy(), tgt_p.numpy(), n_e2e)
@@ -627,6 +634,7 @@ def run_b200(args, w):
                "ms_per_step": 1e3 * t_page,
                "pinned": {"value": w["n"] / t_pin, "ms_per_step": 1e3 * t_pin},
                "fraction_of_device_value": (w["n"] / t_page) / value,
+               "upload_jobs_enqueued_ms": up_ms,
                "timer": "host wall clock around fit+kneighbors(+hub scores) incl. copies, max over ranks"}
         del src_p, tgt_p
 

@@ -72,7 +72,8 @@ __device__ __forceinline__ void emit_flush(const FusedParams &FP, EmitQueue &Q, 
     Q.n -= take;
 }
 
-// tau_col[c0 .. c0+BN) -> registers, lane l holds columns t*32 + l; -inf masks a column.
+// tau_col[c0 .. c0+BN) -> registers, lane l holds columns t*32 + l; -inf masks a column.  The
+// callers stage the NEGATED values in shared memory (column_tile adds them with a packed FMA).
 template <int BN>
 __device__ __forceinline__ void load_taucol(const float *__restrict__ tau_col, int64_t c0,
                                             int64_t y_end, int lane, float (&treg)[BN / 32]) {
@@ -84,25 +85,32 @@ __device__ __forceinline__ void load_taucol(const float *__restrict__ tau_col, i
 }
 
 // One accumulator tile (this warp's 32 TMEM lanes x BN columns), column side.
-// `tk` = this warp's shared copy of the tile's thresholds, xk = x_key of this thread's row
-// (+inf for rows that do not exist: they never emit), row_base = row of lane 0.
+// `ntk` = this warp's shared copy of the tile's NEGATED thresholds (-tau_col; +inf masks a
+// column), xk = x_key of this thread's row (+inf for rows that do not exist: they never emit),
+// row_base = row of lane 0.
 template <int BN>
-__device__ __forceinline__ void column_tile(const FusedParams &FP, EmitQueue &Q, const float *tk,
+__device__ __forceinline__ void column_tile(const FusedParams &FP, EmitQueue &Q, const float *ntk,
                                             uint32_t taddr, int64_t c0, float xk, int64_t row_base,
                                             int lane) {
     constexpr int NCH = BN / 32;
     const float nxk = -xk;
+    const uint32_t ntk_saddr = smem_u32(ntk);
     auto process = [&](const uint32_t (&r)[32], int ch) {
         // g = -2 acc - tau_col;  emit when  key_x - 2 acc < tau_col  <=>  g < -key_x.  The g are
         // not kept (they are recomputed on the rare slow path): the accumulator registers of the
-        // chunk stay the only 32-wide array that is live across the test.
-        auto gval = [&](int j) { return fmaf(-2.f, __uint_as_float(r[j]), -tk[ch * 32 + j]); };
+        // chunk stay the only 32-wide array that is live across the test.  Four at a time:
+        // one broadcast LDS.128 of the negated thresholds + two packed FFMA2 (key_finish4).
+        auto g4 = [&](int j, float &g0, float &g1, float &g2, float &g3) {
+            key_finish4(ntk_saddr + (uint32_t)(ch * 32 + j) * 4u, r[j], r[j + 1], r[j + 2], r[j + 3],
+                        g0, g1, g2, g3);
+        };
         float m4[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            m4[q] = gval(8 * q);
-#pragma unroll
-            for (int j = 1; j < 8; ++j) m4[q] = fminf(m4[q], gval(8 * q + j));
+            float a0, a1, a2, a3, b0, b1, b2, b3;
+            g4(8 * q, a0, a1, a2, a3);
+            g4(8 * q + 4, b0, b1, b2, b3);
+            m4[q] = fminf(fminf(fminf(a0, a1), fminf(a2, a3)), fminf(fminf(b0, b1), fminf(b2, b3)));
         }
         const float gmin = fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
         if (!__any_sync(FULL_MASK, gmin < nxk)) return;
@@ -116,7 +124,14 @@ __device__ __forceinline__ void column_tile(const FusedParams &FP, EmitQueue &Q,
         // that assign the column-buffer slots are in flight together.
         unsigned int m = 0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) m |= (gval(j) < nxk) ? (1u << j) : 0u;
+        for (int j = 0; j < 32; j += 4) {
+            float g0, g1, g2, g3;
+            g4(j, g0, g1, g2, g3);
+            m |= (g0 < nxk) ? (1u << j) : 0u;
+            m |= (g1 < nxk) ? (2u << j) : 0u;
+            m |= (g2 < nxk) ? (4u << j) : 0u;
+            m |= (g3 < nxk) ? (8u << j) : 0u;
+        }
         for (;;) {
             const bool have = m != 0;
             const unsigned int has = __ballot_sync(FULL_MASK, have);

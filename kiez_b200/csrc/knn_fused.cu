@@ -224,7 +224,7 @@ knn_fused_kernel(const __grid_constant__ CUtensorMap map_q_hi,
         // ------------------------------------------------------ column epilogue (R), both CTAs
         const int quad = warp - 4;                         // TMEM lane quadrant
         const int lrow = quad * 32 + lane;
-        float *tk = tile_s + warp * BN;                    // this warp's tau_col tile
+        float *tk = tile_s + warp * BN;                    // this warp's tile of NEGATED tau_col
         EmitQueue Q;
         Q.key = emit_key + quad * EMIT_Q;
         Q.col = emit_col + quad * EMIT_Q;
@@ -246,7 +246,7 @@ knn_fused_kernel(const __grid_constant__ CUtensorMap map_q_hi,
             for (int64_t c0 = y_begin; c0 < y_end; c0 += BN) {
                 __syncwarp();
 #pragma unroll
-                for (int t = 0; t < BN / 32; ++t) tk[t * 32 + lane] = treg[t];
+                for (int t = 0; t < BN / 32; ++t) tk[t * 32 + lane] = -treg[t];
                 __syncwarp();
                 load_taucol<BN>(FP.tau_col, c0 + BN, y_end, lane, treg);
                 mbar_wait(&tmem_full[acc], acc_phase);

@@ -339,7 +339,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap map_q,
         // ------------------------------------------------------ column epilogue, both CTAs
         const int quad = warp - 4;                         // TMEM lane quadrant
         const int lrow = quad * 32 + lane;
-        float *tk = tile_s + warp * BN;                    // this warp's tau_col tile
+        float *tk = tile_s + warp * BN;                    // this warp's tile of NEGATED tau_col
         EmitQueue Q;
         Q.key = emit_key + quad * EMIT_Q;
         Q.col = emit_col + quad * EMIT_Q;
@@ -361,7 +361,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap map_q,
             for (int64_t c0 = y_begin; c0 < y_end; c0 += BN) {
                 __syncwarp();
 #pragma unroll
-                for (int t = 0; t < BN / 32; ++t) tk[t * 32 + lane] = treg[t];
+                for (int t = 0; t < BN / 32; ++t) tk[t * 32 + lane] = -treg[t];
                 __syncwarp();
                 load_taucol<BN>(FP.tau_col, c0 + BN, y_end, lane, treg);
                 mbar_wait(&tmem_full[acc], acc_phase);
@@ -402,12 +402,15 @@ static size_t screen_fixed_smem(int cap, int slots, bool dual) {
 // query chunks.  A fully resident tile gets the remaining units as extra ring slots.
 //
 // `ny` (index rows one list sweeps; 0 = long index): a row accepts ~cap ln(ny / cap) entries
-// whatever the key precision, and every `slots - 4` of them cost one warp-wide list merge.  Over
-// a long index (C4: 1 M rows) that is noise next to the 4096 tensor cycles of an index tile and
-// the shared memory is better spent on residency; over a short one with long lists (C3: cap 112,
-// 100 k rows; C2: cap 56, 15 k rows) the merges ARE the kernel (C3 ran 39 k cycles per tile with
-// 12-slot buffers), so the append buffers grow -- at the price of resident query chunks -- until
-// the estimated merge work per tile drops below a quarter of the tile's tensor time.
+// whatever the key precision, and every `slots - 4` of them cost one warp-wide list merge: a fixed
+// part (call, binary search, two warp barriers: ~100 instructions) plus ~(3 NL + 3 NB + 2)
+// instructions per buffered entry (select.cuh, list_merge).  Only the fixed part depends on the
+// buffer size.  Over a long index (C4: 1 M rows) it is noise next to the 4096 tensor cycles of an
+// index tile and the shared memory is better spent on residency; over a short one with long
+// lists (C3: cap 112, 100 k rows; C2: cap 56, 15 k rows; the threshold sample of the
+// dual-direction pass) the appends ARE the epilogue, so the buffers grow -- 4 KB per step, a
+// quarter of a resident query chunk -- while a step still saves more than ~64 instructions per
+// index tile and warp.
 constexpr int SCREEN_MIN_STAGES = 4;
 static int screen_config(int dpad, int cap, bool dual, int max_smem, int *slots_out,
                          int *resident_out = nullptr, int64_t ny = 0) {
@@ -427,17 +430,20 @@ static int screen_config(int dpad, int cap, bool dual, int max_smem, int *slots_
             min(kchunks + SCREEN_MIN_STAGES, units_for(slots)))
             slots = cand;
     if (ny > 0) {
-        const int regs = cap <= 16 ? 1 : cap <= 32 ? 2 : cap <= 64 ? 4 : 8;      // list_merge<R>
-        const int max_slots = cap <= 16 ? 16 : cap <= 32 ? 32 : 64;
+        const int max_slots = 64;                                                 // list_merge: B <= 64
         const double appends = cap * log(fmax(2.0, (double)ny / cap));            // per row
-        const double merge_instr = 150.0 + 90.0 * regs;                           // warp-wide, per merge
         const double tiles = fmax(1.0, (double)ny / S_BN);
-        auto merge_load = [&](int sl) {      // warp instructions per index tile spent merging
-            return 32.0 * appends / (sl - LISTS_GROUP) * merge_instr / tiles;
+        const double merges_x_slots = 32.0 * appends / tiles;   // merges per tile and warp x (slots - 4)
+        auto saved = [&](int sl) {           // fixed merge instructions per tile saved by sl -> sl + 4
+            return merges_x_slots * 100.0 * (1.0 / (sl - LISTS_GROUP) - 1.0 / sl);
         };
-        while (merge_load(slots) > 1024.0 && slots + LISTS_GROUP <= max_slots &&
+        while (saved(slots) > 64.0 && slots + LISTS_GROUP <= max_slots &&
                units_for(slots + LISTS_GROUP) >= SCREEN_MIN_STAGES)
             slots += LISTS_GROUP;
+    }
+    if (const char *env = getenv("KB2_SCREEN_SLOTS")) {                           // tuning / A-B only
+        const int sl = atoi(env) / LISTS_GROUP * LISTS_GROUP;
+        if (sl >= LISTS_MIN_SLOTS && sl <= 64 && units_for(sl) >= SCREEN_MIN_STAGES) slots = sl;
     }
     const int units = units_for(slots);
     int resident = min(kchunks, units - SCREEN_MIN_STAGES);

@@ -358,6 +358,63 @@ struct RgParams {
     int64_t *out_ind;
 };
 
+// Order-preserving 64-bit integer image of a double: unsigned order == (value ascending, NaN
+// last); -0.0 is folded onto +0.0 first so that equal values stay ties (broken by position).
+__device__ __forceinline__ unsigned long long sortable_bits(double v) {
+    if (isnan(v)) return ~0ull;                           // NaN last (numpy order), ties by position
+    v += 0.0;                                             // -0.0 -> +0.0
+    const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+
+// The k smallest (value, position) pairs of a row held by a full warp (E entries per lane,
+// element e = t * 32 + lane), written in order: k rounds of a warp-wide arg-min on the integer
+// images -- three redux.sync (high word, low word, position) per round, the winner stores its
+// entry and retires it.  For the k <= 16 of 17..256 candidates that kiez asks for this is a third
+// of the instructions of the bitonic sort over lanes x registers (which made the c = 50 / 100
+// rescale kernels instruction-bound at 0.10-0.13 of the HBM roofline).
+constexpr int RG_SELECT_MAX_K = 16;
+template <int E>
+__device__ __forceinline__ void warp_select_topk(const double (&r)[E], const int64_t (&id)[E],
+                                                 int total, bool row_ok, int lane, int k,
+                                                 double *out_dist, int64_t *out_ind) {
+    unsigned long long u[E];
+    unsigned int pos[E];
+#pragma unroll
+    for (int t = 0; t < E; ++t) {
+        const int e = t * 32 + lane;
+        const bool ok = row_ok && e < total;
+        u[t] = ok ? sortable_bits(r[t]) : ~0ull;
+        pos[t] = ok ? (unsigned int)e : 0xFFFFFFFFu;
+    }
+    for (int j = 0; j < k; ++j) {
+        unsigned long long ub = u[0];
+        unsigned int pb = pos[0];
+#pragma unroll
+        for (int t = 1; t < E; ++t) {
+            const bool better = u[t] < ub || (u[t] == ub && pos[t] < pb);
+            ub = better ? u[t] : ub;
+            pb = better ? pos[t] : pb;
+        }
+        const unsigned int hi = (unsigned int)(ub >> 32), lo = (unsigned int)ub;
+        const unsigned int mh = __reduce_min_sync(FULL_MASK, hi);
+        const unsigned int ml = __reduce_min_sync(FULL_MASK, hi == mh ? lo : 0xFFFFFFFFu);
+        const bool match = hi == mh && lo == ml;
+        const unsigned int mp = __reduce_min_sync(FULL_MASK, match ? pb : 0xFFFFFFFFu);
+        if (match && pb == mp && mp != 0xFFFFFFFFu) {      // the one lane that holds the winner
+#pragma unroll
+            for (int t = 0; t < E; ++t) {
+                if (pos[t] == pb) {
+                    out_dist[j] = r[t];
+                    out_ind[j] = id[t];
+                    u[t] = ~0ull;
+                    pos[t] = 0xFFFFFFFFu;
+                }
+            }
+        }
+    }
+}
+
 template <int G, int E>
 __global__ void __launch_bounds__(RG_WARPS * 32)
 rows_rg_kernel(const RgParams p) {
@@ -435,6 +492,13 @@ rows_rg_kernel(const RgParams p) {
         }
         return;
     }
+    if constexpr (G == 32) {
+        if (p.k <= RG_SELECT_MAX_K) {                    // warp-uniform
+            warp_select_topk<E>(r, id, total, row_ok, lane, p.k, p.out_dist + row * p.k,
+                                p.out_ind + row * p.k);
+            return;
+        }
+    }
     int pos[E];
 #pragma unroll
     for (int t = 0; t < E; ++t) {
@@ -502,11 +566,6 @@ row_stats_rg_kernel(const double *__restrict__ dist, int64_t n, int c, double *_
 // shuffles, no divergence) and scatters the k best straight to their final positions; a warp
 // covers 32 consecutive rows, so its loads and stores touch one contiguous span.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long sortable_bits(double v) {
-    if (isnan(v)) return ~0ull;                           // NaN last (numpy order), ties by position
-    const unsigned long long u = (unsigned long long)__double_as_longlong(v);
-    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
-}
 
 // Block = 128 consecutive rows.  Global memory is only touched with coalesced accesses: the
 // block's contiguous span of the (n, c) arrays is copied into shared memory (row stride padded
@@ -515,8 +574,23 @@ __device__ __forceinline__ unsigned long long sortable_bits(double v) {
 constexpr int SMALL_ROWS = 128;
 __host__ __device__ inline int small_stride(int width) { return width | 1; }
 
-template <int C>
-__global__ void __launch_bounds__(SMALL_ROWS)
+// 8-byte asynchronous copy global -> shared (LDGSTS): the staging loop below issues every load of
+// the block's span back to back -- nothing waits in registers for a store, so one DRAM round trip
+// covers the whole span (the register-staged loop of the first version took 2.5 of them and the
+// kernel sat at half the HBM roofline, latency-bound at 30 % occupancy).
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// C = exact row width handled in registers (>= c * nparts), OP = KB2_RESCALE_* / RG_OP_* (a
+// template parameter: the CSLS instance does not pay the registers of the erfc path).
+template <int C, int OP>
+__global__ void __launch_bounds__(SMALL_ROWS, (C <= 10 && OP != KB2_RESCALE_MP_GAUSS) ? 7 : 1)
 rows_small_kernel(const RgParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int total = p.c * p.nparts;
@@ -529,14 +603,13 @@ rows_small_kernel(const RgParams p) {
     for (int part = 0; part < p.nparts; ++part) {
         const double *gd = p.dist + (int64_t)part * p.part_stride + row0 * p.c;
         const int64_t *gi = p.ind + (int64_t)part * p.part_stride + row0 * p.c;
-        // (unrolled: the loads of four iterations are in flight before the first store)
-#pragma unroll 4
         for (int e = threadIdx.x; e < rows_here * p.c; e += SMALL_ROWS) {
             const int r = e / p.c, j = e - r * p.c;
-            sd[r * ld + part * p.c + j] = gd[e];
-            si[r * ld + part * p.c + j] = gi[e];
+            cp_async8(sd + r * ld + part * p.c + j, gd + e);
+            cp_async8(si + r * ld + part * p.c + j, gi + e);
         }
     }
+    cp_async_wait_all();
     __syncthreads();
     const bool row_ok = threadIdx.x < rows_here;
     double x[C];
@@ -550,15 +623,15 @@ rows_small_kernel(const RgParams p) {
             x[e] = sd[threadIdx.x * ld + e];
             id[e] = si[threadIdx.x * ld + e];
             s += x[e];
-            if (!isnan(x[e])) { sn += x[e]; cnt += 1.0; }
+            if (OP == KB2_RESCALE_MP_GAUSS && !isnan(x[e])) { sn += x[e]; cnt += 1.0; }
         }
     }
     double r[C];
-    if (p.op <= KB2_RESCALE_MP_GAUSS) {
+    if constexpr (OP <= KB2_RESCALE_MP_GAUSS) {
         const double mean = s / (double)p.c;                              // ndarray.mean
         double mu = 0.0, sd_row = 0.0, last = 0.0;
-        if (p.op == KB2_RESCALE_LS && row_ok) last = sd[threadIdx.x * ld + p.c - 1];
-        if (p.op == KB2_RESCALE_MP_GAUSS) {                               // nanmean / nanstd(ddof=0)
+        if (OP == KB2_RESCALE_LS && row_ok) last = sd[threadIdx.x * ld + p.c - 1];
+        if constexpr (OP == KB2_RESCALE_MP_GAUSS) {                       // nanmean / nanstd(ddof=0)
             mu = sn / cnt;
             double q = 0.0;
 #pragma unroll
@@ -570,18 +643,18 @@ rows_small_kernel(const RgParams p) {
         for (int e = 0; e < C; ++e) {
             const bool ok = id[e] >= 0 && id[e] < p.n_stats;
             const double a = ok ? __ldg(p.stat_a + id[e]) : qnan;
-            if (p.op == KB2_RESCALE_CSLS) {
+            if constexpr (OP == KB2_RESCALE_CSLS) {
                 r[e] = 2.0 * x[e] - mean - a;
-            } else if (p.op == KB2_RESCALE_LS) {
+            } else if constexpr (OP == KB2_RESCALE_LS) {
                 r[e] = 1.0 - exp(-1.0 * (x[e] * x[e]) / (last * a));
-            } else if (p.op == KB2_RESCALE_NICDM) {
+            } else if constexpr (OP == KB2_RESCALE_NICDM) {
                 r[e] = x[e] / sqrt(mean * a);
             } else {
                 const double sb = ok ? __ldg(p.stat_b + id[e]) : qnan;
                 r[e] = 1.0 - norm_sf(x[e], mu, sd_row) * norm_sf(x[e], a, sb);
             }
         }
-    } else if (p.op == RG_OP_DSL_FINISH) {
+    } else if constexpr (OP == RG_OP_DSL_FINISH) {
         const double mn = *p.gmin;
         const double shift = (mn < 0.0) ? -mn : 0.0;
 #pragma unroll
@@ -643,11 +716,11 @@ row_stats_small_kernel(const double *__restrict__ dist, int64_t n, int c, double
     const int64_t row0 = (int64_t)blockIdx.x * SMALL_ROWS;
     const int rows_here = (int)min((int64_t)SMALL_ROWS, n - row0);
     const double *gd = dist + row0 * c;
-#pragma unroll 4
     for (int e = threadIdx.x; e < rows_here * c; e += SMALL_ROWS) {
         const int r = e / c;
-        sx[r * ld + (e - r * c)] = gd[e];
+        cp_async8(sx + r * ld + (e - r * c), gd + e);
     }
+    cp_async_wait_all();
     __syncthreads();
     if ((int)threadIdx.x >= rows_here) return;
     const int64_t row = row0 + threadIdx.x;
@@ -675,15 +748,27 @@ row_stats_small_kernel(const double *__restrict__ dist, int64_t n, int c, double
 }
 
 constexpr int SMALL_MAX_WIDTH = 16;
-static int launch_rows_small(const RgParams &p, cudaStream_t st) {
+template <int OP>
+static int launch_rows_small_op(const RgParams &p, cudaStream_t st) {
     const int total = p.c * p.nparts;
     const unsigned grid = (unsigned)ceil_div64(p.n, SMALL_ROWS);
     const size_t smem = (size_t)SMALL_ROWS * small_stride(total) * 16;
-    if (total <= 8) rows_small_kernel<8><<<grid, SMALL_ROWS, smem, st>>>(p);
-    else if (total <= 12) rows_small_kernel<12><<<grid, SMALL_ROWS, smem, st>>>(p);
-    else rows_small_kernel<16><<<grid, SMALL_ROWS, smem, st>>>(p);
+    if (total <= 8) rows_small_kernel<8, OP><<<grid, SMALL_ROWS, smem, st>>>(p);
+    else if (total <= 10) rows_small_kernel<10, OP><<<grid, SMALL_ROWS, smem, st>>>(p);   // kiez's default
+    else if (total <= 12) rows_small_kernel<12, OP><<<grid, SMALL_ROWS, smem, st>>>(p);
+    else rows_small_kernel<16, OP><<<grid, SMALL_ROWS, smem, st>>>(p);
     KB2_LAUNCH_CHECK();
     return 0;
+}
+static int launch_rows_small(const RgParams &p, cudaStream_t st) {
+    switch (p.op) {
+        case KB2_RESCALE_CSLS: return launch_rows_small_op<KB2_RESCALE_CSLS>(p, st);
+        case KB2_RESCALE_LS: return launch_rows_small_op<KB2_RESCALE_LS>(p, st);
+        case KB2_RESCALE_NICDM: return launch_rows_small_op<KB2_RESCALE_NICDM>(p, st);
+        case KB2_RESCALE_MP_GAUSS: return launch_rows_small_op<KB2_RESCALE_MP_GAUSS>(p, st);
+        case RG_OP_DSL_FINISH: return launch_rows_small_op<RG_OP_DSL_FINISH>(p, st);
+        default: return launch_rows_small_op<RG_OP_TOPK>(p, st);
+    }
 }
 
 // dispatch on the row width: G lanes x E registers >= width
@@ -714,6 +799,7 @@ struct StatsLauncher {
             const unsigned grid = (unsigned)ceil_div64(n, SMALL_ROWS);
             const size_t smem = (size_t)SMALL_ROWS * small_stride(c) * 8;
             if (c <= 8) row_stats_small_kernel<8><<<grid, SMALL_ROWS, smem, st>>>(dist, n, c, mean, sd, last);
+            else if (c <= 10) row_stats_small_kernel<10><<<grid, SMALL_ROWS, smem, st>>>(dist, n, c, mean, sd, last);
             else if (c <= 12) row_stats_small_kernel<12><<<grid, SMALL_ROWS, smem, st>>>(dist, n, c, mean, sd, last);
             else row_stats_small_kernel<16><<<grid, SMALL_ROWS, smem, st>>>(dist, n, c, mean, sd, last);
             KB2_LAUNCH_CHECK();

@@ -6,8 +6,8 @@
 //   per element : key < tau ?  -> the owner appends (key, col) to its buffer: one
 //                 predicated 64-bit store, no cross-lane traffic, no divergence
 //   per 4 elems : any row's buffer nearly full? -> the whole warp merges that row's
-//                 buffer into its list in registers (sort the buffer, then one bitonic
-//                 merge over lanes x registers), writes the best `cap` back, tightens tau
+//                 buffer into its list by rank (every entry counts the entries below it and
+//                 is scattered to its position), keeps the best `cap`, tightens tau
 //
 // Between merges tau is stale, so a few more elements pass than with an exact
 // threshold, but each costs a store instead of a serialized sorted insert: after the
@@ -45,8 +45,8 @@ struct RowLists {
 
 constexpr int LISTS_GROUP = 4;        // elements offered between two buffer-full checks
 constexpr int LISTS_MIN_SLOTS = 8;    // >= 2 * LISTS_GROUP
-// default: cap/2 rounded up to the group size, within [LISTS_MIN_SLOTS, 64]; list_merge
-// needs B <= 16 for cap <= 16 and B <= 32 for cap <= 32, which this satisfies
+// default: cap/2 rounded up to the group size, within [LISTS_MIN_SLOTS, 64] (list_merge handles
+// cap <= 128 and B <= 64)
 __host__ __device__ inline int lists_buffer_slots(int cap) {
     int b = ((cap / 2 + LISTS_GROUP - 1) / LISTS_GROUP) * LISTS_GROUP;
     return b < LISTS_MIN_SLOTS ? LISTS_MIN_SLOTS : (b > 64 ? 64 : b);
@@ -100,102 +100,73 @@ __device__ __forceinline__ void warp_sort_entries(ent_t (&x)[R], int lane) {
     }
 }
 
-// One register per lane: lanes 0-15 sorted ascending, lanes 16-31 sorted descending
-// (a 16-element bitonic network per half-warp; xor strides <= 8 stay inside the half).
-__device__ __forceinline__ void warp_sort16_halves(ent_t &x, int lane) {
-#pragma unroll
-    for (int size = 2; size <= 16; size <<= 1) {
-#pragma unroll
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            const ent_t other = __shfl_xor_sync(FULL_MASK, x, stride);
-            const bool up = (((lane & 15) & size) == 0) != (lane >= 16);
-            const bool lower = ((lane & stride) == 0);
-            const bool keep_min = (lower == up);
-            const ent_t mn = x < other ? x : other;
-            const ent_t mx = x < other ? other : x;
-            x = keep_min ? mn : mx;
-        }
-    }
-}
-
-// Ascending bitonic MERGE of 32*R entries whose first half is ascending and whose second
-// half is descending (log2(32R) compare-exchange steps instead of a full sort).
-template <int R>
-__device__ __forceinline__ void warp_merge_entries(ent_t (&x)[R], int lane) {
-#pragma unroll
-    for (int stride = 16 * R; stride > 0; stride >>= 1) {
-        if (stride >= 32) {
-            const int rs = stride >> 5;
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                if ((r & rs) == 0) {
-                    const ent_t a = x[r], b = x[r | rs];
-                    x[r] = a < b ? a : b;
-                    x[r | rs] = a < b ? b : a;
-                }
-            }
-        } else {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const ent_t other = __shfl_xor_sync(FULL_MASK, x[r], stride);
-                const bool lower = ((lane & stride) == 0);
-                const ent_t mn = x[r] < other ? x[r] : other;
-                const ent_t mx = x[r] < other ? other : x[r];
-                x[r] = lower ? mn : mx;
-            }
-        }
-    }
-}
-
-// Merge the append buffer (first `cnt` slots valid) of one row into its sorted list:
-// the list (ascending, <= 16R entries) fills the first half of a 32R-entry register
-// tile, the buffer is sorted DESCENDING into the tail of the second half (the rest is
-// +inf), and one bitonic merge yields the ascending union; the best `cap` go back.
+// Merge the append buffer (first `cnt` slots valid, unsorted) of one row into its sorted list BY
+// RANK: every entry computes the position it has in the sorted union and is scattered there.
+//   list entry i (the list is sorted):   position = i + #{buffer entries below it}
+//   buffer entry:                        position = #{list entries below it}  (binary search)
+//                                                 + #{buffer entries below it}
+// Entries are unique ((key, column) pairs; the +inf / -1 padding of a list that is not full yet
+// sits at distinct indices i and only moves up), so the positions are a permutation and the
+// first `cap` of them are written exactly once.  The counting loops are independent compares
+// against broadcast shared-memory reads: ~8 instructions per buffered entry and no dependent
+// shuffle chain.  The bitonic sort + merge over lanes x registers this replaces was 15 (cap 16)
+// to 29 (cap 112) dependent 64-bit shuffle steps, ~3-5 k cycles per merge, and took 42 % of the
+// row-epilogue warps' time at C4 (ncu source view, profiles/r02_ab_experiments.md block R) --
+// those warps are the critical path of the dual-direction kernel.
 // All 32 lanes participate; returns the list's new worst key in every lane.
-// R = 1: cap <= 16, B <= 16 (halves are half-warps).  R >= 2: cap <= 16R, B <= 32*RB.
-template <int R, int RB>
+// NL = list entries per lane (cap <= 32 NL), NB = buffer entries per lane (B <= 32 NB).
+template <int NL, int NB>
 static __device__ __noinline__ float list_merge(ent_t *e, int cap, int cnt, int lane) {
-    ent_t x[R];
-    if constexpr (R == 1) {
-        const int j = lane - 16;
-        x[0] = (lane < cap) ? e[lane] : ((j >= 0 && j < cnt) ? e[cap + j] : EMPTY_ENTRY);
-        warp_sort16_halves(x[0], lane);
-    } else {
-        constexpr int TAIL = 32 * R - 32 * RB;           // first buffer position
+    const ent_t *buf = e + cap;
+    ent_t xl[NL], xb[NB];
+    int pl[NL], pb[NB];
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const int idx = r * 32 + lane;
-            const int j = idx - TAIL;
-            x[r] = (idx < cap) ? e[idx] : ((j >= 0 && j < cnt) ? e[cap + j] : EMPTY_ENTRY);
+    for (int t = 0; t < NL; ++t) {
+        const int i = lane + 32 * t;
+        xl[t] = (i < cap) ? e[i] : EMPTY_ENTRY;
+        pl[t] = (i < cap) ? i : (1 << 30);
+    }
+#pragma unroll
+    for (int u = 0; u < NB; ++u) {
+        const int j = lane + 32 * u;
+        const bool have = j < cnt;
+        xb[u] = have ? buf[j] : EMPTY_ENTRY;
+        int lo = 0;
+        if (have) {                                   // entries of the sorted list below xb[u]
+            int hi = cap;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (e[mid] < xb[u]) lo = mid + 1; else hi = mid;
+            }
         }
-        // descending sort of the buffer registers = ascending sort of the complements
-        ent_t y[RB];
-#pragma unroll
-        for (int r = 0; r < RB; ++r) y[r] = ~x[R - RB + r];
-        warp_sort_entries<RB>(y, lane);
-#pragma unroll
-        for (int r = 0; r < RB; ++r) x[R - RB + r] = ~y[r];
+        pb[u] = have ? lo : (1 << 30);
     }
-    warp_merge_entries<R>(x, lane);
-    ent_t worst = EMPTY_ENTRY;
+    for (int j = 0; j < cnt; ++j) {                   // warp-uniform trip count, broadcast reads
+        const ent_t y = buf[j];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int idx = r * 32 + lane;
-        if (idx < cap) e[idx] = x[r];
-        const ent_t w = __shfl_sync(FULL_MASK, x[r], (cap - 1) & 31);
-        if (r == ((cap - 1) >> 5)) worst = w;
+        for (int t = 0; t < NL; ++t) pl[t] += (y < xl[t]) ? 1 : 0;
+#pragma unroll
+        for (int u = 0; u < NB; ++u) pb[u] += (y < xb[u]) ? 1 : 0;
     }
+    __syncwarp();                                     // every read of the old contents is done
+#pragma unroll
+    for (int t = 0; t < NL; ++t)
+        if (pl[t] < cap) e[pl[t]] = xl[t];
+#pragma unroll
+    for (int u = 0; u < NB; ++u)
+        if (pb[u] < cap) e[pb[u]] = xb[u];
     __syncwarp();
-    return entry_key(worst);
+    return entry_key(e[cap - 1]);
 }
 
+// cap <= 128, B <= 64 (lists_buffer_slots and the screen kernel's plan stay within that)
 __device__ __forceinline__ float list_merge_dispatch(const RowLists &L, int row, int cnt, int lane) {
     ent_t *e = L.ent + (size_t)row * L.stride;
-    if (L.cap <= 16) return list_merge<1, 1>(e, L.cap, cnt, lane);
-    if (L.cap <= 32) return list_merge<2, 1>(e, L.cap, cnt, lane);
+    if (L.cap <= 32)
+        return L.B <= 32 ? list_merge<1, 1>(e, L.cap, cnt, lane) : list_merge<1, 2>(e, L.cap, cnt, lane);
     if (L.cap <= 64)
-        return L.B <= 32 ? list_merge<4, 1>(e, L.cap, cnt, lane) : list_merge<4, 2>(e, L.cap, cnt, lane);
-    return L.B <= 32 ? list_merge<8, 1>(e, L.cap, cnt, lane) : list_merge<8, 2>(e, L.cap, cnt, lane);
+        return L.B <= 32 ? list_merge<2, 1>(e, L.cap, cnt, lane) : list_merge<2, 2>(e, L.cap, cnt, lane);
+    return L.B <= 32 ? list_merge<4, 1>(e, L.cap, cnt, lane) : list_merge<4, 2>(e, L.cap, cnt, lane);
 }
 
 // Merge every row of this warp whose buffer fill satisfies `want` (warp-uniform loop).

@@ -244,6 +244,36 @@ __device__ __forceinline__ void load_ykey(const float *__restrict__ y_key, int64
     }
 }
 
+// Key finish of four accumulator elements against four per-column terms read from shared memory
+// (a warp-uniform address: one broadcast LDS.128):  v[i] = term[i] - 2 acc[i]  as two packed
+// FFMA2 (fma.rn.f32x2: same rounding as fmaf, half the issue slots of the epilogue's hottest
+// loop).  The explicit shared-space load matters too: through the generic `const float *` the
+// compiler emitted generic LD.E.128 for these tiles.
+__device__ __forceinline__ void key_finish4(uint32_t term_saddr, uint32_t a0, uint32_t a1, uint32_t a2,
+                                            uint32_t a3, float &v0, float &v1, float &v2, float &v3) {
+    float t0, t1, t2, t3;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(t0), "=f"(t1), "=f"(t2), "=f"(t3)
+                 : "r"(term_saddr)
+                 : "memory");
+    asm("{\n\t.reg .b64 a, t, m, r;\n\t"
+        "mov.b64 a, {%2, %3};\n\t"
+        "mov.b64 t, {%4, %5};\n\t"
+        "mov.b64 m, {%6, %6};\n\t"
+        "fma.rn.f32x2 r, a, m, t;\n\t"
+        "mov.b64 {%0, %1}, r;\n\t}"
+        : "=f"(v0), "=f"(v1)
+        : "r"(a0), "r"(a1), "f"(t0), "f"(t1), "f"(-2.f));
+    asm("{\n\t.reg .b64 a, t, m, r;\n\t"
+        "mov.b64 a, {%2, %3};\n\t"
+        "mov.b64 t, {%4, %5};\n\t"
+        "mov.b64 m, {%6, %6};\n\t"
+        "fma.rn.f32x2 r, a, m, t;\n\t"
+        "mov.b64 {%0, %1}, r;\n\t}"
+        : "=f"(v2), "=f"(v3)
+        : "r"(a2), "r"(a3), "f"(t2), "f"(t3), "f"(-2.f));
+}
+
 // One accumulator tile (this warp's 32 TMEM lanes x BN columns): key finish + selection.
 // `yk` = this warp's private shared copy of the tile's selection terms.
 template <int BN, bool DOUBLE_BUFFER = true>
@@ -252,11 +282,13 @@ __device__ __forceinline__ void epilogue_tile(const RowLists &L, int lrow, const
                                               int lane) {
     constexpr int NCH = BN / 32;
     uint32_t ra[32];
+    const uint32_t yk_saddr = smem_u32(yk);
     auto process = [&](const uint32_t (&r)[32], int ch) {
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-            v[j] = fmaf(-2.f, __uint_as_float(r[j]), yk[ch * 32 + j]);
+        for (int j = 0; j < 32; j += 4)
+            key_finish4(yk_saddr + (uint32_t)(ch * 32 + j) * 4u, r[j], r[j + 1], r[j + 2], r[j + 3],
+                        v[j], v[j + 1], v[j + 2], v[j + 3]);
         select_chunk<32>(L, lrow, v, (int)(c0 + ch * 32), tau, cnt, lane);
     };
     if constexpr (!DOUBLE_BUFFER) {

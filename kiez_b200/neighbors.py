@@ -16,6 +16,7 @@ graft it onto the *real* ``kiez.neighbors.NNAlgorithm`` when kiez is installed.
 from __future__ import annotations
 
 import os
+import time
 import warnings
 from abc import ABC, abstractmethod
 from typing import Any, Optional, Tuple
@@ -323,6 +324,7 @@ class B200Mixin:
         self._screen_ok = None
         self._screen_boost = False
         self._input_is_numpy = isinstance(source, np.ndarray)
+        self._t_fit_start = time.perf_counter()     # origin of the upload timeline (bench.py e2e)
         self._start_uploads(source, target, only_fit_target)
         return super().fit(source, target, only_fit_target=only_fit_target)
 
@@ -371,7 +373,12 @@ class B200Mixin:
             return
         cosine = self._metric_code == self._lib.METRIC_COSINE
         first = source if not only_fit_target else target      # the matrix that defines the centre
-        if self.center and not cosine and upload.eligible(first):
+        # the strided row sample of the source goes first (it seeds the column thresholds); when
+        # it exists the centre is its mean, taken ON THE DEVICE once it has arrived (_prepare):
+        # a float64 mean over a strided view of a 1 GB host matrix costs ~25 ms of host time
+        # during which nothing would be uploading yet
+        with_sample = any(m is source for m in mats) and target is not None and not only_fit_target
+        if self.center and not cosine and upload.eligible(first) and not with_sample:
             # any vector near the mean serves (distances are translation invariant): the mean
             # of a strided row sample, so that no pass over the whole host matrix is needed
             host = first if isinstance(first, np.ndarray) else first.numpy()
@@ -380,7 +387,7 @@ class B200Mixin:
                 host[::stride].mean(axis=0, dtype=np.float64).astype(np.float32)).to(self.device)
         up = upload.Uploader()
         with torch.cuda.device(self.device):
-            if any(m is source for m in mats) and target is not None and not only_fit_target:
+            if with_sample:
                 cap = candidate_capacity(self.n_candidates)
                 n_s = self._fused_sample_rows(source.shape[0], cap)
                 step = max(1, source.shape[0] // n_s)
@@ -482,7 +489,19 @@ class B200Mixin:
             raise ValueError(f"Expected a 2-d embedding matrix, got shape {tuple(raw.shape)}")
         n, d = raw.shape
         cosine = self._metric_code == lib.METRIC_COSINE
+        sample = getattr(self, "_pending_uploads", {}).pop(("sample", id(data)), None) \
+            if pending is not None else None
+        if self._center_vec is None and self.center and not cosine and sample is not None:
+            # centre = mean of the row sample that was uploaded first (see _start_uploads)
+            job = sample[1]
+            stream = torch.cuda.current_stream(self.device)
+            for chunk in range(len(job.bounds)):
+                job.wait(chunk, stream)
+            self._center_vec = job.dev.mean(dim=0, dtype=torch.float64).to(torch.float32).contiguous()
         if self._center_vec is None and self.center and not cosine and n > 0:
+            if pending is not None:
+                raise RuntimeError("kiez_b200: the centre of a matrix that is still uploading must "
+                                   "come from its host copy or its row sample (_start_uploads)")
             # distances are translation invariant; centring keeps ||y||^2 - 2 q.y well
             # conditioned in fp32 for embeddings far from the origin.  Any vector near the mean
             # serves: the mean of a strided row sample (65536 to 131071 rows of a large matrix)
@@ -500,7 +519,6 @@ class B200Mixin:
         prep = PreparedRows(raw, hi, lo, key, sqn, owner=data, keymax=keymax, err=err, errmax=errmax)
         if pending is not None:
             prep._pending = _PendingRows(self, pending)
-            sample = getattr(self, "_pending_uploads", {}).pop(("sample", id(data)), None)
             if sample is not None:
                 prep.presample = (sample[0], self._prepare_upload(sample[1], owner=data))
             if not lazy:

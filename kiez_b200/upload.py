@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import os
 import threading
+import time
 from concurrent.futures import ThreadPoolExecutor
 from typing import List, Optional, Tuple
 
@@ -27,8 +28,17 @@ CHUNK_BYTES = 32 << 20          # one staging buffer / one async copy
 RING = 3                        # staging buffers in flight
 # the pageable -> pinned memcpy of a chunk is split over this many helper threads (numpy / torch
 # copies release the GIL): torchrun exports OMP_NUM_THREADS=1 to every rank, which would leave a
-# single-threaded memcpy (~6 GB/s) as the bottleneck of the upload
-COPY_THREADS = max(1, min(4, (os.cpu_count() or 4) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+# single-threaded memcpy (~6 GB/s) as the bottleneck of the upload.  Half of the cores this
+# process may use, at most 8 (KB2_COPY_THREADS overrides)
+def _usable_cpus() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):  # pragma: no cover
+        return os.cpu_count() or 4
+
+
+COPY_THREADS = int(os.environ.get("KB2_COPY_THREADS", "0")) or max(
+    1, min(8, _usable_cpus() // 2 // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
 
 _staging = {}                   # (device index, nbytes) -> ([pinned uint8 tensors], [last copy event])
 _copy_streams = {}              # device index -> torch.cuda.Stream
@@ -91,6 +101,7 @@ class HostUpload:
         self.events: List[Optional[torch.cuda.Event]] = [None] * len(self.bounds)
         self.ready = [threading.Event() for _ in self.bounds]
         self.error: Optional[BaseException] = None
+        self.t_enqueued = [0.0] * len(self.bounds)   # time.perf_counter() when chunk i was enqueued
         # the device buffer may be a recycled block that kernels of the consumer's stream still
         # read: the first copy waits for everything enqueued there so far
         self._alloc_event = torch.cuda.Event()
@@ -143,6 +154,7 @@ class HostUpload:
                 if not pinned:
                     ring_events[i % RING] = ev
                 self.events[i] = ev
+                self.t_enqueued[i] = time.perf_counter()
                 self.ready[i].set()
         except BaseException as exc:  # surfaced by wait()
             self.error = exc
