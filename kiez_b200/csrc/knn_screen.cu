@@ -284,14 +284,25 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap map_q,
                     }
                 }
                 __syncwarp();
-                for (int r = 0; r < 32; ++r) {
-                    const int64_t gr = row0 + r;
-                    ent_t *e = L.ent + (size_t)(warp * 32 + r) * L.stride;
-                    for (int p = lane; p < P.cap; p += 32) {
-                        ent_t v = EMPTY_ENTRY;
-                        if (gr < P.nq)
-                            v = pack_entry(__ldcg(P.cand_key + gr * P.cap + p), __ldcg(P.cand_idx + gr * P.cap + p));
-                        e[p] = v;
+                // 16 rows per batch: their 32 loads are issued before the first store.  (Written
+                // row by row the compiler kept load -> generic store -> load: one L2 round trip
+                // per row and 32-entry slice, 25-50 k cycles at the start of every unit while the
+                // MMA issuer waited for the first accumulator to be consumed.)
+                constexpr int SEED_ROWS = 16;
+                for (int p = lane; p < P.cap; p += 32) {
+                    for (int r0 = 0; r0 < 32; r0 += SEED_ROWS) {
+                        float sk[SEED_ROWS];
+                        int si[SEED_ROWS];
+#pragma unroll
+                        for (int j = 0; j < SEED_ROWS; ++j) {
+                            const int64_t gr = row0 + r0 + j;
+                            const bool ok = gr < P.nq;
+                            sk[j] = ok ? __ldcg(P.cand_key + gr * P.cap + p) : INFINITY;
+                            si[j] = ok ? __ldcg(P.cand_idx + gr * P.cap + p) : -1;
+                        }
+#pragma unroll
+                        for (int j = 0; j < SEED_ROWS; ++j)      // pack(+inf, -1) == EMPTY_ENTRY
+                            L.ent[(size_t)(warp * 32 + r0 + j) * L.stride + p] = pack_entry(sk[j], si[j]);
                     }
                 }
                 __syncwarp();
@@ -402,15 +413,12 @@ static size_t screen_fixed_smem(int cap, int slots, bool dual) {
 // query chunks.  A fully resident tile gets the remaining units as extra ring slots.
 //
 // `ny` (index rows one list sweeps; 0 = long index): a row accepts ~cap ln(ny / cap) entries
-// whatever the key precision, and every `slots - 4` of them cost one warp-wide list merge: a fixed
-// part (call, binary search, two warp barriers: ~100 instructions) plus ~(3 NL + 3 NB + 2)
-// instructions per buffered entry (select.cuh, list_merge).  Only the fixed part depends on the
-// buffer size.  Over a long index (C4: 1 M rows) it is noise next to the 4096 tensor cycles of an
-// index tile and the shared memory is better spent on residency; over a short one with long
-// lists (C3: cap 112, 100 k rows; C2: cap 56, 15 k rows; the threshold sample of the
-// dual-direction pass) the appends ARE the epilogue, so the buffers grow -- 4 KB per step, a
-// quarter of a resident query chunk -- while a step still saves more than ~64 instructions per
-// index tile and warp.
+// whatever the key precision, and every `slots - 4` of them cost one warp-wide list merge.  Over
+// a long index (C4: 1 M rows) that is noise next to the 4096 tensor cycles of an index tile and
+// the shared memory is better spent on residency; over a short one with long lists (C3: cap 112,
+// 100 k rows; C2: cap 56, 15 k rows) the merges ARE the kernel (C3 ran 39 k cycles per tile with
+// 12-slot buffers), so the append buffers grow -- at the price of resident query chunks -- until
+// the estimated merge work per tile drops below a quarter of the tile's tensor time.
 constexpr int SCREEN_MIN_STAGES = 4;
 static int screen_config(int dpad, int cap, bool dual, int max_smem, int *slots_out,
                          int *resident_out = nullptr, int64_t ny = 0) {
@@ -430,14 +438,15 @@ static int screen_config(int dpad, int cap, bool dual, int max_smem, int *slots_
             min(kchunks + SCREEN_MIN_STAGES, units_for(slots)))
             slots = cand;
     if (ny > 0) {
-        const int max_slots = 64;                                                 // list_merge: B <= 64
+        const int regs = cap <= 16 ? 1 : cap <= 32 ? 2 : cap <= 64 ? 4 : 8;      // merge cost class
+        const int max_slots = cap <= 16 ? 16 : cap <= 32 ? 32 : 64;
         const double appends = cap * log(fmax(2.0, (double)ny / cap));            // per row
+        const double merge_instr = 150.0 + 90.0 * regs;                           // warp-wide, per merge
         const double tiles = fmax(1.0, (double)ny / S_BN);
-        const double merges_x_slots = 32.0 * appends / tiles;   // merges per tile and warp x (slots - 4)
-        auto saved = [&](int sl) {           // fixed merge instructions per tile saved by sl -> sl + 4
-            return merges_x_slots * 100.0 * (1.0 / (sl - LISTS_GROUP) - 1.0 / sl);
+        auto merge_load = [&](int sl) {      // warp instructions per index tile spent merging
+            return 32.0 * appends / (sl - LISTS_GROUP) * merge_instr / tiles;
         };
-        while (saved(slots) > 64.0 && slots + LISTS_GROUP <= max_slots &&
+        while (merge_load(slots) > 1024.0 && slots + LISTS_GROUP <= max_slots &&
                units_for(slots + LISTS_GROUP) >= SCREEN_MIN_STAGES)
             slots += LISTS_GROUP;
     }
