@@ -51,6 +51,7 @@ struct ScreenParams {
     int64_t nq, ny;
     int kchunks, cap, buf_slots, stages;
     int resident;         // K chunks of the query tile kept in shared memory (<= kchunks)
+    int rank_max;         // lists > 32: buffered entries up to which a merge goes by rank (select.cuh)
     int steps;            // index ranges
     int chained;          // 1: ranges of a query tile run in order and carry its lists
     int64_t per_step;     // index rows per range (multiple of S_BN)
@@ -94,6 +95,7 @@ knn_screen_kernel(const __grid_constant__ CUtensorMap map_q,
     L.cap = P.cap;
     L.B = P.buf_slots;
     L.stride = lists_stride(P.cap, P.buf_slots);
+    L.rank_max = P.rank_max;
     L.ent = reinterpret_cast<ent_t *>(tile_s + EPI_WARPS * BN + (DUAL ? EMIT_WORDS : 0));
     uint64_t *bars = reinterpret_cast<uint64_t *>(L.ent + (size_t)BM * L.stride);
     uint64_t *full_bar = bars;                         // [stages]   used in CTA 0
@@ -567,6 +569,11 @@ extern "C" int kb2_knn_screen(const float *q_hi, const float *q_key, int64_t nq,
                              chained ? ny : P.per_step);
     KB2_CHECK(P.stages > 0, "knn_screen: dpad=%d cap=%d is not supported (dpad <= %d, multiple of "
               "%d, cap <= 128; see kb2_screen_stages)", dpad, cap, S_MAX_DPAD, S_BK);
+    P.rank_max = LISTS_RANK_MAX_CNT;
+    if (const char *env = getenv("KB2_RANK_MAX_CNT")) {                           // tuning / A-B only
+        const int r = atoi(env);
+        if (r >= 0 && r <= 64) P.rank_max = r;
+    }
     if (const char *env = getenv("KB2_SCREEN_STAGES")) {
         const int s = atoi(env);
         if (s >= 3 && s <= P.stages) P.stages = s;

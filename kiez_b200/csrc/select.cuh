@@ -37,11 +37,14 @@ __device__ __forceinline__ int entry_col(ent_t e) { return (int)(unsigned)(e & 0
 // +inf key, column -1
 constexpr ent_t EMPTY_ENTRY = ((ent_t)0xFF800000u << 32) | 0xFFFFFFFFull;
 
+constexpr int LISTS_RANK_MAX_CNT = 12;   // see list_merge_dispatch
+
 struct RowLists {
     ent_t *ent;     // [rows][stride]: [0,cap) sorted list, [cap, cap+B) append buffer
     int cap;
     int B;          // buffer slots, >= LISTS_MIN_SLOTS
     int stride;     // cap + B entries per row
+    int rank_max = LISTS_RANK_MAX_CNT;   // lists > 32: merge by rank up to this many buffered entries
 };
 
 constexpr int LISTS_GROUP = 4;        // elements offered between two buffer-full checks
@@ -249,18 +252,21 @@ static __device__ __noinline__ float list_merge_bitonic(ent_t *e, int cap, int c
 
 // cap <= 128, B <= 64.  Lists of <= 32 always merge by rank; longer ones only while the buffer
 // holds few entries (the flush at the end of an index range, sparse steady state).
-constexpr int LISTS_RANK_MAX_CNT = 12;
 __device__ __forceinline__ float list_merge_dispatch(const RowLists &L, int row, int cnt, int lane) {
     ent_t *e = L.ent + (size_t)row * L.stride;
     if (L.cap <= 32)
         return L.B <= 32 ? list_merge_rank<1, 1>(e, L.cap, cnt, lane)
                          : list_merge_rank<1, 2>(e, L.cap, cnt, lane);
     if (L.cap <= 64) {
-        if (cnt <= LISTS_RANK_MAX_CNT) return list_merge_rank<2, 1>(e, L.cap, cnt, lane);
+        if (cnt <= L.rank_max)
+            return cnt <= 32 ? list_merge_rank<2, 1>(e, L.cap, cnt, lane)
+                             : list_merge_rank<2, 2>(e, L.cap, cnt, lane);
         return L.B <= 32 ? list_merge_bitonic<4, 1>(e, L.cap, cnt, lane)
                          : list_merge_bitonic<4, 2>(e, L.cap, cnt, lane);
     }
-    if (cnt <= LISTS_RANK_MAX_CNT) return list_merge_rank<4, 1>(e, L.cap, cnt, lane);
+    if (cnt <= L.rank_max)
+        return cnt <= 32 ? list_merge_rank<4, 1>(e, L.cap, cnt, lane)
+                         : list_merge_rank<4, 2>(e, L.cap, cnt, lane);
     return L.B <= 32 ? list_merge_bitonic<8, 1>(e, L.cap, cnt, lane)
                      : list_merge_bitonic<8, 2>(e, L.cap, cnt, lane);
 }
