@@ -595,6 +595,10 @@ def run_b200(args, w):
     if rank == 0:
         try:
             roofline["tf32_cublas_tflops_live"] = tf32_cublas_tflops(device)
+            # `frac` uses the driver's sustained bf16 figure / 2; under the power cap a TF32 GEMM
+            # sustains a little more than half the bf16 rate, so the fraction of what cuBLAS
+            # reaches in this very run is reported next to it
+            roofline["frac_of_live_cublas"] = mmas * achieved / roofline["tf32_cublas_tflops_live"]
         except Exception as exc:  # pragma: no cover
             roofline["tf32_cublas_tflops_live"] = f"failed: {exc}"
 
