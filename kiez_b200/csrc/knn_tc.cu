@@ -9,7 +9,7 @@
 // This file: ONE CTA per (128-row query tile, index split) work unit, persistent over
 // the units.  CTA = 6 warps:
 //   warps 0-3  epilogue: tcgen05.ld their 32 TMEM lanes (one query row per thread),
-//              key finish + threshold test + buffered append / bitonic merge (select.cuh)
+//              key finish + threshold test + buffered append / merge by rank (select.cuh)
 //   warp  4    TMA producer: one K chunk (BK features = one swizzle row) of
 //              {q_hi, q_lo, y_hi, y_lo} per pipeline stage
 //   warp  5    MMA issuer: 3 products x BK/8 UMMA_K steps per stage into one of two

@@ -1,7 +1,8 @@
 // Hubness-reduction rescaling of the candidate distances, fused with the final
-// top-k sort.  All kernels are one-warp-per-row, float64, HBM-bound: they stream
-// the (n, c) candidate arrays once, gather 1-2 per-target statistics per element
-// and write (n, k).
+// top-k sort.  All kernels are float64 and HBM-bound: they stream the (n, c) candidate
+// arrays once, gather 1-2 per-target statistics per element and write (n, k).  Rows of
+// <= 16 values: one thread per row (rows_small_kernel); <= 256: a row per lane group in
+// registers (rows_rg_kernel); longer: one warp per row in shared memory.
 //   CSLS        kiez/hubness_reduction/csls.py:85-96
 //   LS / NICDM  kiez/hubness_reduction/local_scaling.py:129-151
 //   MP Gaussian kiez/hubness_reduction/mutual_proximity.py:166-183 (numpy branch:

@@ -3,8 +3,9 @@
 // per lane (element e = t*G + lane_in_group, so every load is coalesced).  Reductions are
 // xor-shuffles inside the group; the top-k sort is a bitonic network over lanes x registers
 // keyed by (value, position) with NaN last -- the order numpy's argsort/argpartition give
-// (kiez/hubness_reduction/base.py:80-87).  No shared memory, no block barriers: with c = 10
-// a warp handles two rows in ~150 instructions and the kernels run at HBM speed.
+// (kiez/hubness_reduction/base.py:80-87).  No shared memory, no block barriers.  (Rows of <= 16
+// values take the thread-per-row kernels of rescale.cu instead, and k <= 16 of a wider row are
+// selected by arg-min rounds, rescale.cu warp_select_topk.)
 #pragma once
 #include "common.cuh"
 
